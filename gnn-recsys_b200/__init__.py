@@ -1,0 +1,8 @@
+"""B200-native embedding + recommendation hot path of hieucnm/GNN-RecSys.
+
+Import as ``gnn_recsys_b200`` (the repo-root alias module) -- the directory name carries a hyphen.
+"""
+from .graph import HeteroGraph, Block, Relation, heterograph, edge_graph, csr_by_dst_host, NID, EID  # noqa: F401
+from .synthetic import make_graph, SyntheticData, CONFIGS  # noqa: F401
+from .dataloading import (MultiLayerFullNeighborSampler, MultiLayerNeighborSampler, NodeDataLoader,  # noqa: F401
+                          EdgeDataLoader, negative_sampler, to_block)

@@ -1,0 +1,291 @@
+"""Block construction on the host: samplers and loaders feeding the hot path.
+
+Mirrors the ``dgl.dataloading`` surface the reference uses (``main_inference.py:126-138``,
+``src/sampling.py:153-241``): ``MultiLayerFullNeighborSampler``, ``MultiLayerNeighborSampler``,
+``NodeDataLoader``, ``EdgeDataLoader`` and ``negative_sampler.Uniform``. Sampling itself is outside the
+accelerated path; these classes exist so the reference's call sites keep working
+and so that config 4 (fan-out [10, 10] blocks + 1024 positive / 1024*K negative edges) has inputs.
+
+Block layout follows DGL's ``to_block``: destination nodes = seeds in the given order; source nodes =
+the destination nodes first, then unseen edge sources in first-appearance order (canonical etype
+order, then edge-id order). ``NodeDataLoader(..., batch_size=None)`` -- the fast path -- yields a single
+full-graph block per layer instead of ``ceil(n/128)`` sampled mini-batches; for a full-neighbour
+sampler the embeddings of the seed nodes are identical.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .graph import Block, HeteroGraph, Relation, NID, EID, _as_np_ids
+
+
+def _first_appearance_unique(arrs: List[np.ndarray]) -> np.ndarray:
+    cat = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.int64)
+    if cat.size == 0:
+        return cat.astype(np.int64)
+    uniq, first = np.unique(cat, return_index=True)
+    return uniq[np.argsort(first, kind='stable')].astype(np.int64)
+
+
+def _relabel(ids: np.ndarray, space: np.ndarray) -> np.ndarray:
+    """Position of each ``ids`` value inside ``space`` (``space`` holds unique values, any order)."""
+    if ids.size == 0:
+        return ids.astype(np.int64)
+    order = np.argsort(space, kind='stable')
+    pos = np.searchsorted(space[order], ids)
+    return order[pos].astype(np.int64)
+
+
+class _FrontierSampler:
+    """Shared block builder; subclasses choose which in-edges of the seeds form the frontier."""
+
+    def __init__(self, num_layers: int):
+        self.num_layers = num_layers
+
+    def _pick(self, layer: int, n_slots_per_row: np.ndarray, rng) -> Optional[np.ndarray]:
+        return None  # None = keep every slot (full neighbourhood)
+
+    def frontier(self, g: HeteroGraph, seeds: Dict[str, np.ndarray], layer: int, rng, exclude=None):
+        """Per canonical etype: (src ids, dst ids, edge ids) of the chosen in-edges, edge-id order."""
+        out = {}
+        for c in g.canonical_etypes:
+            s, d = g.edge_arrays(c)
+            sd = seeds.get(c[2])
+            if sd is None or sd.size == 0 or s.size == 0:
+                out[c] = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64))
+                continue
+            indptr, _, eperm = g.csr(c)
+            rows = np.unique(sd)
+            lo, hi = indptr[rows].astype(np.int64), indptr[rows + 1].astype(np.int64)
+            deg = hi - lo
+            slots = np.repeat(lo - np.cumsum(deg) + deg, deg) + np.arange(int(deg.sum()))
+            eids = eperm[slots].astype(np.int64)
+            if exclude is not None and c in exclude and exclude[c].size:
+                keep = ~np.isin(eids, exclude[c])
+                eids = eids[keep]
+                row_of = np.repeat(np.arange(rows.size), deg)[keep]
+                deg = np.bincount(row_of, minlength=rows.size)
+            fan = self._fanout(layer)
+            if fan is not None and eids.size:
+                row_of = np.repeat(np.arange(rows.size), deg)
+                key = rng.random(eids.size)
+                order = np.lexsort((key, row_of))
+                start = np.cumsum(deg) - deg
+                rank = np.arange(eids.size) - np.repeat(start, deg)
+                eids = eids[order][rank < fan]
+            eids = np.sort(eids)
+            out[c] = (s[eids].astype(np.int64), d[eids].astype(np.int64), eids)
+        return out
+
+    def _fanout(self, layer: int):
+        return None
+
+    def sample_blocks(self, g: HeteroGraph, seed_nodes: Dict[str, np.ndarray], rng=None, exclude=None,
+                      edge_weight: Optional[str] = None) -> List[Block]:
+        rng = rng if rng is not None else np.random.default_rng(0)
+        seeds = {t: _as_np_ids(v).astype(np.int64) for t, v in seed_nodes.items()}
+        blocks: List[Block] = []
+        for layer in reversed(range(self.num_layers)):
+            fr = self.frontier(g, seeds, layer, rng, exclude)
+            blocks.insert(0, to_block(g, fr, seeds, edge_weight))
+            seeds = {t: blocks[0].srcnodes[t].data[NID].numpy() for t in blocks[0].srctypes}
+        return blocks
+
+
+def to_block(g: HeteroGraph, frontier, dst_nodes: Dict[str, np.ndarray], edge_weight: Optional[str] = None) -> Block:
+    """Compact a frontier into a ``Block`` (DGL ``to_block`` semantics, see module docstring)."""
+    src_ids = {}
+    for t in g.ntypes:
+        parts = [dst_nodes[t]] if t in dst_nodes else []
+        parts += [fr[0] for c, fr in frontier.items() if c[0] == t]
+        src_ids[t] = _first_appearance_unique(parts)
+    rels = {}
+    for c, (s, d, eids) in frontier.items():
+        dn = dst_nodes.get(c[2], np.zeros(0, np.int64))
+        ls, ld = _relabel(s, src_ids[c[0]]), _relabel(d, dn)
+        order = np.argsort(ld, kind='stable')
+        indptr = np.zeros(dn.size + 1, dtype=np.int64)
+        np.cumsum(np.bincount(ld, minlength=dn.size), out=indptr[1:])
+        w = None
+        if edge_weight is not None and edge_weight in g.edges[c].data:
+            w = g.edges[c].data[edge_weight].detach().cpu().to(torch.float32).reshape(-1)[
+                torch.from_numpy(eids[order])].contiguous()
+        rels[c] = Relation(torch.from_numpy(indptr.astype(np.int32)), torch.from_numpy(ls[order].astype(np.int32)),
+                           int(src_ids[c[0]].size), int(dn.size), torch.from_numpy(eids[order]), w)
+    num_src = {t: int(src_ids[t].size) for t in g.ntypes}
+    num_dst = {t: int(dst_nodes[t].size) if t in dst_nodes else 0 for t in g.ntypes}
+    sf, df = {}, {}
+    for t in g.ntypes:
+        sid = torch.from_numpy(src_ids[t])
+        did = torch.from_numpy(dst_nodes[t]) if t in dst_nodes else torch.zeros(0, dtype=torch.int64)
+        sf[t] = {k: v[sid] for k, v in g.nodes[t].data.items()}
+        sf[t][NID] = sid
+        df[t] = {k: v[did] for k, v in g.nodes[t].data.items()}
+        df[t][NID] = did
+    return Block(rels, num_src, num_dst, sf, df)
+
+
+class MultiLayerFullNeighborSampler(_FrontierSampler):
+    """``dgl.dataloading.MultiLayerFullNeighborSampler`` (``main_inference.py:129``)."""
+
+
+class MultiLayerNeighborSampler(_FrontierSampler):
+    """``dgl.dataloading.MultiLayerNeighborSampler(fanouts, replace=False)`` (``src/sampling.py:159``):
+    at most ``fanouts[layer]`` in-edges per seed node and relation, drawn uniformly without replacement."""
+
+    def __init__(self, fanouts, replace=False):
+        super().__init__(len(fanouts))
+        if replace:
+            raise NotImplementedError('replace=True is not used by the reference')
+        self.fanouts = list(fanouts)
+
+    def _fanout(self, layer):
+        return self.fanouts[layer]
+
+
+class NodeDataLoader:
+    """``dgl.dataloading.NodeDataLoader`` surface: iterate ``(input_nodes, output_nodes, blocks)``.
+
+    ``batch_size=None`` (or >= number of seeds) with a full-neighbour sampler takes the fast path: one
+    iteration whose blocks are full-graph blocks; ``get_embeddings`` then keeps only the seeded rows.
+    """
+
+    def __init__(self, g: HeteroGraph, nids, block_sampler, batch_size=None, shuffle=False, drop_last=False,
+                 num_workers=0, seed=0, edge_weight=None, **kwargs):
+        self.g, self.sampler = g, block_sampler
+        self.nids = {t: _as_np_ids(v).astype(np.int64) for t, v in nids.items()}
+        self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
+        self.rng = np.random.default_rng(seed)
+        self.edge_weight = edge_weight
+        self._flat_t = np.concatenate([np.full(v.size, i) for i, (t, v) in enumerate(sorted(self.nids.items()))]) \
+            if self.nids else np.zeros(0, np.int64)
+        self._flat_i = np.concatenate([v for _, v in sorted(self.nids.items())]) if self.nids else np.zeros(0, np.int64)
+        self._types = [t for t, _ in sorted(self.nids.items())]
+
+    @property
+    def full_graph(self) -> bool:
+        return (self.batch_size is None or self.batch_size >= self._flat_i.size) and \
+            isinstance(self.sampler, MultiLayerFullNeighborSampler)
+
+    def __len__(self):
+        n = self._flat_i.size
+        if self.batch_size is None:
+            return 1
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        if self.full_graph:
+            blk = self.g.full_block(self.edge_weight)
+            blocks = [blk] * self.sampler.num_layers
+            ids = {t: torch.arange(self.g.num_nodes(t)) for t in self.g.ntypes}
+            yield ids, {t: torch.from_numpy(v) for t, v in self.nids.items()}, blocks
+            return
+        n = self._flat_i.size
+        order = self.rng.permutation(n) if self.shuffle else np.arange(n)
+        for b in range(len(self)):
+            sel = order[b * self.batch_size:(b + 1) * self.batch_size]
+            seeds = {}
+            for ti, t in enumerate(self._types):
+                ids = self._flat_i[sel[self._flat_t[sel] == ti]]
+                if ids.size:
+                    seeds[t] = ids
+            blocks = self.sampler.sample_blocks(self.g, seeds, self.rng, edge_weight=self.edge_weight)
+            yield ({t: blocks[0].srcnodes[t].data[NID] for t in blocks[0].srctypes},
+                   {t: blocks[-1].dstnodes[t].data[NID] for t in blocks[-1].dsttypes}, blocks)
+
+
+class _Uniform:
+    """``negative_sampler.Uniform(k)``: per positive edge (u, v) of etype (s, r, d): k edges
+    (u, randint(0, num_nodes(d))), laid out k-consecutive (``src/model.py:516`` depends on that layout)."""
+
+    def __init__(self, k):
+        self.k = k
+
+    def __call__(self, g: HeteroGraph, eids_dict, rng):
+        out = {}
+        for c, eids in eids_dict.items():
+            c = g.to_canonical_etype(c)
+            s, _ = g.edge_arrays(c)
+            src = np.repeat(s[_as_np_ids(eids).astype(np.int64)].astype(np.int64), self.k)
+            out[c] = (src, rng.integers(0, g.num_nodes(c[2]), size=src.size, dtype=np.int64))
+        return out
+
+
+class negative_sampler:  # noqa: N801 - mirrors the dgl module name
+    Uniform = _Uniform
+
+
+class EdgeDataLoader:
+    """``dgl.dataloading.EdgeDataLoader`` surface (``src/sampling.py:168-207``): iterate
+    ``(input_nodes, pos_g, neg_g, blocks)``. ``pos_g`` / ``neg_g`` are compacted onto the batch's seed nodes
+    (first-appearance order over [pos, neg] x etypes x (src, dst)), which are also the destination nodes of
+    ``blocks[-1]``. ``exclude='reverse_types'`` drops the batch edges and their reverse-relation twins
+    (same edge id) from the blocks."""
+
+    def __init__(self, g: HeteroGraph, eids, block_sampler, g_sampling=None, exclude=None, reverse_etypes=None,
+                 negative_sampler=None, batch_size=1, shuffle=False, drop_last=False, num_workers=0, seed=0,
+                 pin_memory=False, **kwargs):
+        self.g, self.g_sampling = g, (g_sampling if g_sampling is not None else g)
+        self.sampler, self.neg = block_sampler, negative_sampler
+        self.exclude, self.reverse_etypes = exclude, reverse_etypes or {}
+        self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
+        self.rng = np.random.default_rng(seed)
+        self.eids = {g.to_canonical_etype(c): _as_np_ids(v).astype(np.int64) for c, v in eids.items()}
+        self._types = sorted(self.eids)
+        self._flat_t = np.concatenate([np.full(self.eids[c].size, i) for i, c in enumerate(self._types)])
+        self._flat_e = np.concatenate([self.eids[c] for c in self._types])
+
+    def __len__(self):
+        n = self._flat_e.size
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        g = self.g
+        n = self._flat_e.size
+        order = self.rng.permutation(n) if self.shuffle else np.arange(n)
+        for b in range(len(self)):
+            sel = order[b * self.batch_size:(b + 1) * self.batch_size]
+            items = {c: self._flat_e[sel[self._flat_t[sel] == i]] for i, c in enumerate(self._types)}
+            items = {c: e for c, e in items.items() if e.size}
+            pos = {c: (g.edge_arrays(c)[0][e].astype(np.int64), g.edge_arrays(c)[1][e].astype(np.int64))
+                   for c, e in items.items()}
+            neg = self.neg(g, items, self.rng) if self.neg is not None else {}
+            space = {}
+            for t in g.ntypes:
+                parts = []
+                for edges in (pos, neg):
+                    for c in g.canonical_etypes:
+                        if c in edges:
+                            if c[0] == t:
+                                parts.append(edges[c][0])
+                            if c[2] == t:
+                                parts.append(edges[c][1])
+                space[t] = _first_appearance_unique(parts)
+            sizes = {t: int(space[t].size) for t in g.ntypes}
+
+            def compact(edges):
+                data = {}
+                for c in g.canonical_etypes:
+                    s, d = edges.get(c, (np.zeros(0, np.int64), np.zeros(0, np.int64)))
+                    data[c] = (_relabel(s, space[c[0]]), _relabel(d, space[c[2]]))
+                cg = HeteroGraph(data, sizes)
+                for t in g.ntypes:
+                    cg.nodes[t].data[NID] = torch.from_numpy(space[t])
+                return cg
+
+            pos_g, neg_g = compact(pos), compact(neg)
+            for c, e in items.items():
+                pos_g.edges[c].data[EID] = torch.from_numpy(e)
+            exclude = None
+            if self.exclude == 'reverse_types':
+                exclude = {}
+                for c, e in items.items():
+                    exclude[c] = np.concatenate([exclude.get(c, np.zeros(0, np.int64)), e])
+                    rc = g.to_canonical_etype(self.reverse_etypes[c[1]])
+                    exclude[rc] = np.concatenate([exclude.get(rc, np.zeros(0, np.int64)), e])
+            seeds = {t: v for t, v in space.items() if v.size}
+            blocks = self.sampler.sample_blocks(self.g_sampling, seeds, self.rng, exclude)
+            yield ({t: blocks[0].srcnodes[t].data[NID] for t in blocks[0].srctypes}, pos_g, neg_g, blocks)

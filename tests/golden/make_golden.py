@@ -1,0 +1,205 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE's own code.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference's unmodified ``src/model.py`` (ConvModel, max_margin_loss), ``src/train/run.py::get_embeddings``
+and ``src/metrics.py::{get_recs, create_already_bought}`` are imported from /root/reference and executed on CPU
+over ``oracle/dgl_shim`` (DGL 0.5.2 is not installable here -- see the shim's docstring for what that pins
+and what it does not). Inputs, weights and outputs of every case are written to ``<case>.npz``; the tests
+compare the oracle (tests/test_oracle.py) and the CUDA path (tests/test_gpu_parity.py) against them.
+"""
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get('GNN_RECSYS_REFERENCE', '/root/reference')
+sys.path[:0] = [os.path.join(ROOT, 'oracle', 'dgl_shim'), REFERENCE, ROOT]
+
+import dgl  # noqa: E402  (the shim)
+from src.model import ConvModel, max_margin_loss  # noqa: E402  (reference, verbatim)
+from src.train.run import get_embeddings  # noqa: E402
+from src.metrics import get_recs, create_already_bought  # noqa: E402
+
+import gnn_recsys_b200 as grb  # noqa: E402  (host-side containers only: synthetic data + block building)
+
+REL = [('user', 'buys', 'item'), ('item', 'bought-by', 'user'), ('user', 'clicks', 'item'), ('item', 'clicked-by', 'user')]
+
+
+def tiny_data(n_users, n_items, n_edges, seed):
+    """Synthetic graph plus the engineered edge cases of SURVEY.md 8c: an item and a user without
+    in-edges, duplicate edges, a hub item, a user whose only edge is a click."""
+    d = grb.make_graph(n_users, n_items, n_edges, seed)
+    users, items, is_buy = d.users.copy(), d.items.copy(), d.is_buy.copy()
+    lonely_item, lonely_user, hub = 3, 5, 7
+    items[items == lonely_item] = hub                    # item 3 has no in-edges; item 7 becomes a hub
+    users[users == lonely_user] = (lonely_user + 1) % n_users   # user 5 has no edges at all
+    users[2:6], items[2:6], is_buy[2:6] = users[2], items[2], True   # 4 duplicate purchases
+    d.users, d.items, d.is_buy = users, items, is_buy
+    return d
+
+
+def shim_graph(d, occurrence=False, seed=0):
+    rel = d.relations()
+    g = dgl.heterograph({c: (torch.from_numpy(s.astype(np.int64)), torch.from_numpy(t.astype(np.int64)))
+                         for c, (s, t) in rel.items()}, {'user': d.n_users, 'item': d.n_items})
+    g.nodes['user'].data['features'] = d.user_feat
+    g.nodes['item'].data['features'] = d.item_feat
+    occ = {}
+    if occurrence:
+        rng = np.random.default_rng(seed + 100)
+        nb, nc = int(d.is_buy.sum()), int((~d.is_buy).sum())
+        occ = {'buys': rng.integers(1, 5, nb), 'clicks': rng.integers(1, 5, nc)}
+        occ['bought-by'], occ['clicked-by'] = occ['buys'], occ['clicks']
+        for et, v in occ.items():
+            g.edges[et].data['occurrence'] = torch.from_numpy(v.astype(np.int64))  # src/utils_data.py:304-315
+    return g, occ
+
+
+def to_shim_block(b):
+    """product Block -> shim block (structure only; same local ids, CSR slot order)."""
+    edges, ef = {}, {}
+    for c, r in b.rels.items():
+        dst = torch.repeat_interleave(torch.arange(r.n_dst), (r.indptr[1:] - r.indptr[:-1]).long())
+        edges[c] = (r.indices.long(), dst)
+        ef[c] = {} if r.weight is None else {'occurrence': r.weight}
+    sf = {t: dict(f) for t, f in b._src_frames.items()}
+    df = {t: dict(f) for t, f in b._dst_frames.items()}
+    return dgl.DGLHeteroGraph(edges, b.num_src, b.num_dst, is_block=True, src_frames=sf, dst_frames=df, edge_frames=ef)
+
+
+def save_case(name, meta, arrays):
+    flat = {'meta': np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
+    for k, v in arrays.items():
+        flat[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **flat)
+    print('wrote %-34s %7.1f KB' % (name + '.npz', os.path.getsize(path) / 1024))
+
+
+def edges_arrays(d, occ):
+    out = {}
+    for c, (s, t) in d.relations().items():
+        out['edges/%s/src' % c[1]] = s.astype(np.int64)
+        out['edges/%s/dst' % c[1]] = t.astype(np.int64)
+    for et, v in occ.items():
+        out['occurrence/%s' % et] = v.astype(np.int64)
+    out['user_feat'], out['item_feat'] = d.user_feat, d.item_feat
+    return out
+
+
+def embedding_case(name, n_users, n_items, n_edges, seed, n_layers, hidden, out, aggregator, norm=True,
+                   embedding_layer=True, hetero='sum', k=10, batched=None, sub_users=None):
+    d = tiny_data(n_users, n_items, n_edges, seed)
+    occ_on = aggregator.endswith('_edge')
+    g, occ = shim_graph(d, occ_on, seed)
+    torch.manual_seed(seed + 1)
+    dim_dict = {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}
+    model = ConvModel(g, n_layers, dim_dict, norm, 0.0, aggregator, 'cos', hetero, embedding_layer)
+    model.eval()
+    conv_layers = n_layers - 1 if embedding_layer else n_layers
+    uids = np.arange(n_users) if sub_users is None else np.asarray(sub_users)
+    nids = {'user': torch.from_numpy(uids), 'item': torch.arange(n_items)}
+    sampler = dgl.dataloading.MultiLayerFullNeighborSampler(conv_layers)
+    bs = (n_users + n_items) if batched is None else batched
+    torch.manual_seed(seed + 2)
+    loader = dgl.dataloading.NodeDataLoader(g, nids, sampler, batch_size=bs, shuffle=batched is not None, drop_last=False)
+    with torch.no_grad(), redirect_stdout(io.StringIO()):
+        y = get_embeddings(g, out, model, loader, len(loader), False, None, embedding_layer)   # reference code
+        bought_eids = g.out_edges(u=torch.from_numpy(uids), form='eid', etype='buys')          # main_inference.py:98
+        bought = create_already_bought(g, bought_eids)                                         # reference code
+        recs = get_recs(g, y, model, out, k, uids.tolist(), bought, remove_already_bought=True,
+                        cuda=False, device=None, pred='cos', use_popularity=False)             # reference code
+        recs_keep = get_recs(g, y, model, out, k, uids.tolist()[:8], bought, remove_already_bought=False)
+    rec_arr = np.full((uids.size, k), -1, dtype=np.int64)
+    for r, u in enumerate(uids.tolist()):
+        rec_arr[r, :len(recs[u])] = np.asarray(recs[u], dtype=np.int64)
+    keep_arr = np.stack([np.asarray(recs_keep[u][:k], dtype=np.int64) for u in uids.tolist()[:8]])
+    meta = dict(name=name, n_users=n_users, n_items=n_items, n_layers=n_layers, hidden=hidden, out=out,
+                aggregator=aggregator, norm=norm, embedding_layer=embedding_layer, hetero=hetero, k=k,
+                batched=batched, seed=seed)
+    arrays = edges_arrays(d, occ)
+    arrays.update({'sd/' + kk: v for kk, v in model.state_dict().items()})
+    arrays.update({'emb/user': y['user'], 'emb/item': y['item'], 'user_ids': uids, 'recs': rec_arr, 'recs_keep': keep_arr})
+    save_case(name, meta, arrays)
+    return d, g, model
+
+
+def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, batch, neg_k, aggregator='mean'):
+    """Config-4 style training-step forward: sampled blocks + positive/negative edge scoring + loss."""
+    d = tiny_data(n_users, n_items, n_edges, seed)
+    g, _ = shim_graph(d)
+    pg = d.graph()
+    torch.manual_seed(seed + 1)
+    n_layers = len(fanouts) + 1
+    model = ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, aggregator,
+                      'cos', 'sum', True)
+    model.eval()
+    sampler = grb.MultiLayerNeighborSampler(fanouts)
+    eids = {'buys': np.arange(pg.num_edges('buys')), 'clicks': np.arange(pg.num_edges('clicks'))}
+    loader = grb.EdgeDataLoader(pg, eids, sampler, exclude='reverse_types',
+                                reverse_etypes={'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by',
+                                                'clicked-by': 'clicks'},
+                                negative_sampler=grb.negative_sampler.Uniform(neg_k), batch_size=batch, shuffle=True,
+                                seed=seed + 2)
+    _, pos_g, neg_g, blocks = next(iter(loader))
+    sblocks = [to_shim_block(b) for b in blocks]
+    sizes = {t: blocks[-1].num_dst[t] for t in pg.ntypes}
+
+    def shim_pair(pgp):
+        return dgl.DGLHeteroGraph({c: tuple(torch.from_numpy(np.asarray(a, dtype=np.int64)) for a in pgp.edge_arrays(c))
+                                   for c in pgp.canonical_etypes}, sizes, sizes)
+    with torch.no_grad():
+        feats = sblocks[0].srcdata['features']
+        h, pos, neg = model(sblocks, feats, shim_pair(pos_g), shim_pair(neg_g), True)          # reference code
+        loss = max_margin_loss(pos, neg, 0.266, neg_k)                                          # reference code
+    arrays = {'sd/' + kk: v for kk, v in model.state_dict().items()}
+    for li, b in enumerate(blocks):
+        for t in pg.ntypes:
+            arrays['block%d/nsrc/%s' % (li, t)] = np.int64(b.num_src[t])
+            arrays['block%d/ndst/%s' % (li, t)] = np.int64(b.num_dst[t])
+            arrays['block%d/srcid/%s' % (li, t)] = b.srcnodes[t].data[grb.NID]
+        for c, r in b.rels.items():
+            arrays['block%d/indptr/%s' % (li, c[1])] = r.indptr
+            arrays['block%d/indices/%s' % (li, c[1])] = r.indices
+    for t in pg.ntypes:
+        arrays['feat/' + t] = blocks[0].srcnodes[t].data['features']
+        arrays['h/' + t] = h[t]
+    for c in pg.canonical_etypes:
+        for nm, gg, sc in (('pos', pos_g, pos), ('neg', neg_g, neg)):
+            s, t = gg.edge_arrays(c)
+            arrays['%s/%s/src' % (nm, c[1])], arrays['%s/%s/dst' % (nm, c[1])] = s, t
+            arrays['%s/%s/score' % (nm, c[1])] = sc[c]
+    arrays['loss'] = loss
+    meta = dict(name=name, n_layers=n_layers, hidden=hidden, out=out, aggregator=aggregator, neg_k=neg_k, delta=0.266,
+                n_blocks=len(blocks), seed=seed)
+    save_case(name, meta, arrays)
+
+
+def main():
+    T = dict(n_users=50, n_items=20, n_edges=300)
+    for agg in ('mean', 'mean_nn', 'pool_nn', 'mean_edge', 'pool_nn_edge'):
+        embedding_case('tiny_%s' % agg, seed=3, n_layers=3, hidden=16, out=8, aggregator=agg, **T)
+    embedding_case('tiny_mean_nonorm', seed=4, n_layers=2, hidden=16, out=8, aggregator='mean', norm=False, **T)
+    embedding_case('tiny_mean_noembed', seed=5, n_layers=2, hidden=16, out=8, aggregator='mean', embedding_layer=False, **T)
+    embedding_case('tiny_pool_hetero_max', seed=6, n_layers=3, hidden=16, out=8, aggregator='pool_nn', hetero='max', **T)
+    embedding_case('tiny_mean_hetero_mean', seed=7, n_layers=2, hidden=16, out=8, aggregator='mean', hetero='mean', **T)
+    # the reference's real batching (128 nodes, shuffle) must equal the one-block-per-layer pass for seeded rows
+    embedding_case('tiny_mean_batched', seed=8, n_layers=3, hidden=16, out=8, aggregator='mean', batched=16,
+                   sub_users=list(range(0, 50, 2)), **T)
+    # model-sized dims of configs c1/c2 (2-layer mean 128/128) and c3 (3-layer pool_nn hidden 256)
+    embedding_case('small_mean_128', 400, 150, 6000, seed=9, n_layers=2, hidden=128, out=128, aggregator='mean')
+    embedding_case('small_pool_256', 200, 80, 3000, seed=10, n_layers=3, hidden=256, out=128, aggregator='pool_nn')
+    forward_case('fwd_fanout_mean', 300, 120, 5000, seed=11, hidden=32, out=16, fanouts=[10, 10], batch=64, neg_k=20)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,49 @@
+"""Shared test helpers: golden-fixture loading and tie-aware top-k comparison."""
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+RELS = [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]
+EMBED_CASES = ['tiny_mean', 'tiny_mean_nn', 'tiny_pool_nn', 'tiny_mean_edge', 'tiny_pool_nn_edge', 'tiny_mean_nonorm',
+               'tiny_mean_noembed', 'tiny_pool_hetero_max', 'tiny_mean_hetero_mean', 'tiny_mean_batched',
+               'small_mean_128', 'small_pool_256']
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    return meta, z
+
+
+def state_dict(z):
+    return {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd/')}
+
+
+def case_relations(z):
+    rel = {}
+    for c in RELS:
+        rel[c] = (z['edges/%s/src' % c[1]], z['edges/%s/dst' % c[1]])
+    return rel
+
+
+def case_occurrence(z):
+    return {c: z['occurrence/%s' % c[1]] for c in RELS if 'occurrence/%s' % c[1] in z.files}
+
+
+def assert_topk_equivalent(got, want, scores, k, tol=1e-5):
+    """``got`` / ``want``: [n, k] item ids (-1 = empty). Rows must agree position by position except where the
+    fp32 scores of the two ids differ by less than ``tol`` (ties are unordered in the reference: np.argsort)."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    for r in range(got.shape[0]):
+        if np.array_equal(got[r], want[r]):
+            continue
+        assert np.array_equal(got[r] < 0, want[r] < 0), 'row %d: different number of recommendations' % r
+        valid = want[r] >= 0
+        sg, sw = scores[r, got[r][valid]], scores[r, want[r][valid]]
+        assert np.all(np.abs(sg - sw) < tol), 'row %d: ids differ beyond score ties: %s vs %s' % (r, got[r], want[r])
+        assert len(set(got[r][valid].tolist())) == int(valid.sum()), 'row %d: duplicate ids' % r

@@ -1,0 +1,86 @@
+"""The straight-line oracle against the golden fixtures produced by the reference's own code."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import EMBED_CASES, load_case, state_dict, case_relations, case_occurrence, assert_topk_equivalent
+from oracle import straightline as O
+
+
+def full_blocks(meta, z):
+    rel, occ = case_relations(z), case_occurrence(z)
+    num = {'user': meta['n_users'], 'item': meta['n_items']}
+    blk = O.block_from_coo(num, num, {c: (s, d, occ.get(c)) for c, (s, d) in rel.items()})
+    n_conv = meta['n_layers'] - 1 if meta['embedding_layer'] else meta['n_layers']
+    return num, [blk] * n_conv
+
+
+@pytest.mark.parametrize('name', EMBED_CASES)
+def test_embeddings_match_reference(name):
+    meta, z = load_case(name)
+    num, blocks = full_blocks(meta, z)
+    feats = {'user': torch.from_numpy(z['user_feat']), 'item': torch.from_numpy(z['item_feat'])}
+    seeds = {'user': z['user_ids'], 'item': np.arange(meta['n_items'])}
+    y = O.get_embeddings_full(num, blocks, feats, state_dict(z), meta['out'], seeds, meta['aggregator'], meta['norm'],
+                              meta['hetero'], meta['embedding_layer'])
+    for t in ('user', 'item'):
+        np.testing.assert_allclose(y[t].numpy(), z['emb/' + t], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', EMBED_CASES)
+def test_recs_match_reference(name):
+    meta, z = load_case(name)
+    hu, hi = torch.from_numpy(z['emb/user']), torch.from_numpy(z['emb/item'])
+    buys = case_relations(z)[('user', 'buys', 'item')]
+    bought = O.create_already_bought(buys[0], buys[1])
+    uids = z['user_ids'].tolist()
+    recs = O.get_recs(hu, hi, meta['k'], uids, bought)
+    got = np.full((len(uids), meta['k']), -1, dtype=np.int64)
+    for r, u in enumerate(uids):
+        got[r, :len(recs[u])] = recs[u]
+    scores = O.get_recs_scores(hu, hi, uids).numpy()
+    assert_topk_equivalent(got, z['recs'], scores, meta['k'])
+    # vectorised variant (the "fair" CPU baseline) gives the same answer up to ties
+    order = np.lexsort((buys[1], buys[0]))
+    indptr = np.zeros(meta['n_users'] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(buys[0], minlength=meta['n_users']), out=indptr[1:])
+    vec = O.get_recs_vectorised(hu, hi, meta['k'], uids, indptr, buys[1][order])
+    assert_topk_equivalent(vec, z['recs'], scores, meta['k'])
+
+
+def test_forward_scores_and_loss_match_reference():
+    meta, z = load_case('fwd_fanout_mean')
+    blocks = []
+    for li in range(meta['n_blocks']):
+        ns = {t: int(z['block%d/nsrc/%s' % (li, t)]) for t in ('user', 'item')}
+        nd = {t: int(z['block%d/ndst/%s' % (li, t)]) for t in ('user', 'item')}
+        rels = {}
+        for c in [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]:
+            indptr, indices = z['block%d/indptr/%s' % (li, c[1])], z['block%d/indices/%s' % (li, c[1])]
+            dst = np.repeat(np.arange(indptr.size - 1), np.diff(indptr))
+            rels[c] = (indices.astype(np.int64), dst, None)
+        blocks.append(O.block_from_coo(ns, nd, rels))
+    feats = {t: torch.from_numpy(z['feat/' + t]) for t in ('user', 'item')}
+    cets = [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]
+    pos = {c: (z['pos/%s/src' % c[1]], z['pos/%s/dst' % c[1]]) for c in cets}
+    neg = {c: (z['neg/%s/src' % c[1]], z['neg/%s/dst' % c[1]]) for c in cets}
+    h, ps, ns_ = O.model_forward(blocks, feats, pos, neg, state_dict(z), meta['aggregator'])
+    for t in ('user', 'item'):
+        np.testing.assert_allclose(h[t].numpy(), z['h/' + t], rtol=1e-4, atol=1e-5)
+    for c in cets:
+        np.testing.assert_allclose(ps[c].numpy(), z['pos/%s/score' % c[1]], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(ns_[c].numpy(), z['neg/%s/score' % c[1]], rtol=1e-4, atol=1e-5)
+    loss = O.max_margin_loss(ps, ns_, meta['delta'], meta['neg_k'])
+    np.testing.assert_allclose(float(loss), float(z['loss']), rtol=1e-5)
+
+
+def test_csr_and_first_appearance():
+    rng = np.random.default_rng(0)
+    src, dst = rng.integers(0, 30, 200), rng.integers(0, 17, 200)
+    indptr, indices, eperm = O.csr_by_dst(src, dst, 17)
+    assert indptr[-1] == 200 and np.all(np.diff(indptr) == np.bincount(dst, minlength=17))
+    for v in range(17):
+        seg = eperm[indptr[v]:indptr[v + 1]]
+        assert np.all(np.diff(seg) > 0) and np.all(dst[seg] == v) and np.all(src[seg] == indices[indptr[v]:indptr[v + 1]])
+    ids, uniq = O.first_appearance_ids(['b', 'a', 'b', 'c', 'a'])
+    assert ids.tolist() == [0, 1, 0, 2, 1] and uniq == ['b', 'a', 'c']
