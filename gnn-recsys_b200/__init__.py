@@ -6,3 +6,9 @@ from .graph import HeteroGraph, Block, Relation, heterograph, edge_graph, csr_by
 from .synthetic import make_graph, SyntheticData, CONFIGS  # noqa: F401
 from .dataloading import (MultiLayerFullNeighborSampler, MultiLayerNeighborSampler, NodeDataLoader,  # noqa: F401
                           EdgeDataLoader, negative_sampler, to_block)
+from .model import (ConvModel, ConvLayer, NodeEmbedding, HeteroGraphConv, CosinePrediction,  # noqa: F401
+                    max_margin_loss)
+from .train.run import get_embeddings  # noqa: F401
+from .metrics import get_recs, get_recs_tensor, create_already_bought, create_already_bought_csr  # noqa: F401
+from .recs import RecsConfig, BoughtCSR, ScoringTable, recommend_topk  # noqa: F401
+from . import ops, _native  # noqa: F401

@@ -1,0 +1,442 @@
+// The CUDA-core stages around the tcgen05 scoring kernel of get_recs (reference src/metrics.py:52-77):
+//   gr_colmean_normalized_f32  mean of the L2-normalised rows (the item "centre")
+//   gr_score_prep              normalise (- centre), pad, round to bf16 / fp16, optional hi/lo split
+//   gr_rescore_topk_f32        exact fp32 cosine of the shortlist, final top-k, soundness proof per user
+//   gr_score_topk_exact_f32    exact fp32 scoring of all items for listed users (fallback + brute-force checker)
+//   gr_topk_merge              row-wise merge of partial (score, id) lists
+// Cosine follows nn.CosineSimilarity(dim=1, eps) as the reference calls it (src/metrics.py:58-59):
+//   x.y / sqrt(max(|x|^2 |y|^2, eps^2)).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+using gr::FULL;
+
+// ------------------------------------------------------------------------------------------------ colmean
+constexpr int CM_MAXQ = 8;  // columns per lane: d <= 256
+
+__global__ void __launch_bounds__(256) colmean_partial_kernel(const float* __restrict__ x, long long n, int d,
+                                                              float* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float acc[CM_MAXQ];
+#pragma unroll
+  for (int q = 0; q < CM_MAXQ; ++q) acc[q] = 0.f;
+  for (long long r = warp; r < n; r += n_warps) {
+    float v[CM_MAXQ];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < CM_MAXQ; ++q) {
+      const int c = lane + 32 * q;
+      v[q] = c < d ? __ldg(x + r * d + c) : 0.f;
+      ss = fmaf(v[q], v[q], ss);
+    }
+    const float inv = 1.f / fmaxf(sqrtf(gr::warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int q = 0; q < CM_MAXQ; ++q) acc[q] = fmaf(v[q], inv, acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < CM_MAXQ; ++q) {
+    const int c = lane + 32 * q;
+    if (c < d) partials[warp * d + c] = acc[q];
+  }
+}
+
+__global__ void colmean_final_kernel(const float* __restrict__ partials, long long n_partials, long long n, int d,
+                                     float* __restrict__ center) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float a = 0.f;
+  for (long long p = 0; p < n_partials; ++p) a += partials[p * d + c];
+  center[c] = n > 0 ? a / (float)n : 0.f;
+}
+
+int colmean_grid() { return gr::sm_count() * 4; }
+
+// ------------------------------------------------------------------------------------------------ prep
+__device__ __forceinline__ uint16_t to16(float v, int elem_type) {
+  if (elem_type == GR_ELEM_FP16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float from16(uint16_t b, int elem_type) {
+  if (elem_type == GR_ELEM_FP16) return __half2float(__ushort_as_half(b));
+  return __bfloat162float(__ushort_as_bfloat16(b));
+}
+
+__global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict__ x, long long n, int d,
+                                                         const float* __restrict__ center, int d_pad, int parts,
+                                                         int elem_type, uint16_t* __restrict__ out,
+                                                         float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nq = d_pad / 32;  // 2 or 4
+  float max_norm = 0.f, min_norm = INFINITY;
+  for (long long r = warp; r < n; r += n_warps) {
+    float v[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      v[q] = (q < nq && c < d) ? __ldg(x + r * d + c) : 0.f;
+      ss = fmaf(v[q], v[q], ss);
+    }
+    const float nrm = sqrtf(gr::warp_sum(ss));
+    if (nrm > 0.f) min_norm = fminf(min_norm, nrm);
+    const float inv = 1.f / fmaxf(nrm, 1e-12f);
+    float cs = 0.f;
+    uint16_t* o = out + r * (long long)(parts * d_pad);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      if (q < nq) {
+        float w = v[q] * inv;
+        if (center != nullptr && c < d) w -= __ldg(center + c);
+        if (c >= d) w = 0.f;
+        cs = fmaf(w, w, cs);
+        const uint16_t hi = to16(w, elem_type);
+        o[c] = hi;
+        if (parts == 2) o[d_pad + c] = to16(w - from16(hi, elem_type), elem_type);
+      }
+    }
+    max_norm = fmaxf(max_norm, sqrtf(gr::warp_sum(cs)));
+  }
+  if (stats != nullptr && lane == 0) {
+    atomicMax(reinterpret_cast<int*>(stats), __float_as_int(max_norm));        // non-negative floats order as ints
+    if (min_norm < INFINITY) atomicMin(reinterpret_cast<int*>(stats + 1), __float_as_int(min_norm));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ exact cosine
+__device__ __forceinline__ void dot_norm(const float* __restrict__ a, const float* __restrict__ b, int d, float& dot,
+                                         float& nb) {
+  dot = 0.f; nb = 0.f;
+  if ((d & 3) == 0) {
+    for (int c = 0; c < d; c += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(a + c);
+      const float4 y = gr::ldg_f4(b + c);
+      dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot); dot = fmaf(x.z, y.z, dot); dot = fmaf(x.w, y.w, dot);
+      nb = fmaf(y.x, y.x, nb); nb = fmaf(y.y, y.y, nb); nb = fmaf(y.z, y.z, nb); nb = fmaf(y.w, y.w, nb);
+    }
+  } else {
+    for (int c = 0; c < d; ++c) {
+      const float x = a[c], y = __ldg(b + c);
+      dot = fmaf(x, y, dot); nb = fmaf(y, y, nb);
+    }
+  }
+}
+__device__ __forceinline__ float cosine(float dot, float na, float nb, float eps) {
+  return dot / sqrtf(fmaxf(na * nb, eps * eps));
+}
+
+// better(a, b): a precedes b in the output order (score descending, id ascending)
+__device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
+
+// ------------------------------------------------------------------------------------------------ rescore
+constexpr int RS_WARPS = 8;
+
+__global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
+    const float* __restrict__ hu, const float* __restrict__ hi, long long item_id_base, int d,
+    const float* __restrict__ center, const float* __restrict__ sl_score, const int* __restrict__ sl_id, int S,
+    long long n_users, const float* __restrict__ stats, float err_rel, float err_abs, float tie_tol, int k, float eps,
+    int* __restrict__ out_ids, float* __restrict__ out_scores, int* __restrict__ overflow_users,
+    int* __restrict__ n_overflow) {
+  extern __shared__ __align__(16) float s_user[];  // [RS_WARPS][d]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* xu = s_user + w * d;
+  for (long long u = (long long)blockIdx.x * RS_WARPS + w; u < n_users; u += (long long)gridDim.x * RS_WARPS) {
+    float pn = 0.f, pc = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float x = __ldg(hu + u * d + c);
+      xu[c] = x;
+      pn = fmaf(x, x, pn);
+      if (center != nullptr) pc = fmaf(x, __ldg(center + c), pc);
+    }
+    const float nu = gr::warp_sum(pn);
+    const float xc = gr::warp_sum(pc) / fmaxf(sqrtf(nu), 1e-12f);
+    __syncwarp();
+    int id = -1;
+    float approx = -INFINITY, e = -INFINITY;
+    if (lane < S) {
+      id = sl_id[u * S + lane];
+      approx = sl_score[u * S + lane];
+    }
+    if (id >= 0) {
+      float dot, ni;
+      dot_norm(xu, hi + (id - item_id_base) * (long long)d, d, dot, ni);
+      e = cosine(dot, nu, ni, eps);
+    }
+    const bool valid = id >= 0;
+    int rank = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const float ei = __shfl_sync(FULL, e, i);
+      const int ii = __shfl_sync(FULL, id, i);
+      if (ii >= 0 && i != lane && better(ei, ii, e, id)) ++rank;
+    }
+    const int n_valid = __popc(__ballot_sync(FULL, valid));
+    if (valid && rank < k) {
+      out_ids[u * k + rank] = id;
+      out_scores[u * k + rank] = e;
+    }
+    if (lane >= n_valid && lane < k) {
+      out_ids[u * k + lane] = -1;
+      out_scores[u * k + lane] = -INFINITY;
+    }
+    // soundness: a full shortlist may have cut off items that score within the quantisation error of its tail
+    if (n_valid == S) {
+      const float tau = __shfl_sync(FULL, approx, S - 1);
+      const unsigned kth_mask = __ballot_sync(FULL, valid && rank == k - 1);
+      float kth = -INFINITY;
+      if (kth_mask) kth = __shfl_sync(FULL, e, __ffs(kth_mask) - 1);
+      const float bound = tau + err_rel * stats[0] + err_abs + xc;
+      const float min_item = stats[1];
+      const bool clamp_binds = nu > 0.f && nu * min_item * min_item < eps * eps;
+      if (lane == 0 && (S < k || kth < bound - tie_tol || clamp_binds)) {
+        const int slot = atomicAdd(n_overflow, 1);
+        overflow_users[slot] = (int)u;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ exact top-k
+constexpr int EX_THREADS = 256;
+
+__global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
+    const float* __restrict__ hu, const int* __restrict__ user_list, const int* __restrict__ n_list, long long n_users,
+    const float* __restrict__ hi, long long n_items, long long item_id_base, int d,
+    const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int k, float eps,
+    int* __restrict__ out_ids, float* __restrict__ out_scores) {
+  extern __shared__ __align__(16) float smem[];
+  float* xu = smem;                                            // [d_al]
+  const int d_al = (d + 3) & ~3;
+  float* ls = xu + d_al;                                       // [k][EX_THREADS]
+  int* li = reinterpret_cast<int*>(ls + k * EX_THREADS);       // [k][EX_THREADS]
+  __shared__ float red_s[EX_THREADS / 32];
+  __shared__ int red_i[EX_THREADS / 32];
+  __shared__ int red_t[EX_THREADS / 32];
+  __shared__ float s_nu;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const long long count = n_list != nullptr ? (long long)*n_list : n_users;
+  for (long long idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const long long u = user_list != nullptr ? (long long)user_list[idx] : idx;
+    __syncthreads();
+    float pn = 0.f;
+    for (int c = tid; c < d; c += EX_THREADS) {
+      const float x = hu[u * d + c];
+      xu[c] = x;
+      pn = fmaf(x, x, pn);
+    }
+    pn = gr::warp_sum(pn);
+    if (lane == 0) red_s[w] = pn;
+    for (int s = 0; s < k; ++s) { ls[s * EX_THREADS + tid] = -INFINITY; li[s * EX_THREADS + tid] = -1; }
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f;
+      for (int i = 0; i < EX_THREADS / 32; ++i) a += red_s[i];
+      s_nu = a;
+    }
+    __syncthreads();
+    const float nu = s_nu;
+    long long b0 = 0, b1 = 0;
+    if (bought_indptr != nullptr) { b0 = bought_indptr[u]; b1 = bought_indptr[u + 1]; }
+    float tau = -INFINITY;
+    for (long long i = tid; i < n_items; i += EX_THREADS) {
+      float dot, ni;
+      dot_norm(xu, hi + i * d, d, dot, ni);
+      const float s = cosine(dot, nu, ni, eps);
+      if (s > tau) {
+        const int gid = (int)(item_id_base + i);
+        long long lo = b0, hi_ = b1;
+        while (lo < hi_) {
+          const long long mid = (lo + hi_) >> 1;
+          if (bought_ids[mid] < gid) lo = mid + 1; else hi_ = mid;
+        }
+        if (lo < b1 && bought_ids[lo] == gid) continue;
+        int j = k - 1;
+        while (j > 0 && ls[(j - 1) * EX_THREADS + tid] < s) {
+          ls[j * EX_THREADS + tid] = ls[(j - 1) * EX_THREADS + tid];
+          li[j * EX_THREADS + tid] = li[(j - 1) * EX_THREADS + tid];
+          --j;
+        }
+        ls[j * EX_THREADS + tid] = s;
+        li[j * EX_THREADS + tid] = gid;
+        tau = ls[(k - 1) * EX_THREADS + tid];
+      }
+    }
+    // merge the 256 sorted per-thread lists: k rounds of block-wide argmax over the list heads
+    int head = 0;
+    for (int r = 0; r < k; ++r) {
+      float s = head < k ? ls[head * EX_THREADS + tid] : -INFINITY;
+      int id = head < k ? li[head * EX_THREADS + tid] : -1;
+      if (id < 0) { s = -INFINITY; id = 0x7fffffff; }
+      int who = tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(FULL, s, o);
+        const int i2 = __shfl_xor_sync(FULL, id, o);
+        const int w2 = __shfl_xor_sync(FULL, who, o);
+        if (better(s2, i2, s, id)) { s = s2; id = i2; who = w2; }
+      }
+      if (lane == 0) { red_s[w] = s; red_i[w] = id; red_t[w] = who; }
+      __syncthreads();
+      float bs = red_s[0];
+      int bi = red_i[0], bt = red_t[0];
+      for (int i = 1; i < EX_THREADS / 32; ++i)
+        if (better(red_s[i], red_i[i], bs, bi)) { bs = red_s[i]; bi = red_i[i]; bt = red_t[i]; }
+      const bool none = bi == 0x7fffffff;
+      if (tid == 0) {
+        out_ids[u * k + r] = none ? -1 : bi;
+        out_scores[u * k + r] = none ? -INFINITY : bs;
+      }
+      if (!none && tid == bt) ++head;
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ merge
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ scores, const int* __restrict__ ids,
+                                                         int parts, long long n_users, int k_in, int k_out,
+                                                         float* __restrict__ out_scores, int* __restrict__ out_ids) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long u = warp; u < n_users; u += n_warps) {
+    const float* ps = scores + ((long long)lane * n_users + u) * k_in;  // lane p walks list p
+    const int* pi = ids + ((long long)lane * n_users + u) * k_in;
+    int head = 0;
+    float hs = -INFINITY;
+    int hid = 0x7fffffff;
+    auto load_head = [&]() {
+      hs = -INFINITY; hid = 0x7fffffff;
+      if (lane < parts && head < k_in) {
+        const int id = pi[head];
+        if (id >= 0) { hid = id; hs = ps[head]; }
+      }
+    };
+    load_head();
+    for (int r = 0; r < k_out; ++r) {
+      float s = hs;
+      int id = hid, who = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(FULL, s, o);
+        const int i2 = __shfl_xor_sync(FULL, id, o);
+        const int w2 = __shfl_xor_sync(FULL, who, o);
+        if (better(s2, i2, s, id) || (s2 == s && i2 == id && w2 < who)) { s = s2; id = i2; who = w2; }
+      }
+      const bool none = id == 0x7fffffff;
+      if (lane == 0) {
+        out_ids[u * k_out + r] = none ? -1 : id;
+        out_scores[u * k_out + r] = none ? -INFINITY : s;
+      }
+      if (!none && lane == who) { ++head; load_head(); }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" size_t gr_colmean_workspace_bytes(int64_t n, int32_t d) {
+  (void)n;
+  return gr::align_up((size_t)colmean_grid() * 8 * (size_t)std::max(d, 1) * sizeof(float), 256);
+}
+
+extern "C" int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, float* center, void* ws,
+                                         size_t ws_bytes, gr_stream_t stream) {
+  GR_REQUIRE(n >= 0 && d > 0 && d <= 32 * CM_MAXQ, GR_E_INVALID, "d must be in [1, 256]");
+  GR_REQUIRE(center != nullptr && (n == 0 || x != nullptr), GR_E_INVALID, "null pointer");
+  GR_REQUIRE(ws != nullptr && ws_bytes >= gr_colmean_workspace_bytes(n, d), GR_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = colmean_grid();
+  float* partials = static_cast<float*>(ws);
+  colmean_partial_kernel<<<grid, 256, 0, st>>>(x, n, d, partials);
+  GR_LAUNCH_CHECK();
+  colmean_final_kernel<<<(d + 127) / 128, 128, 0, st>>>(partials, (long long)grid * 8, n, d, center);
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}
+
+extern "C" int gr_score_prep(const float* x, int64_t n, int32_t d, const float* center_or_null, int32_t d_pad,
+                             int32_t parts, int32_t elem_type, uint16_t* out_q, float* stats_or_null,
+                             gr_stream_t stream) {
+  GR_REQUIRE(n >= 0 && d > 0, GR_E_INVALID, "bad shape");
+  GR_REQUIRE(d_pad == 64 || d_pad == 128, GR_E_INVALID, "d_pad must be 64 or 128");
+  GR_REQUIRE(d <= d_pad, GR_E_INVALID, "d exceeds d_pad");
+  GR_REQUIRE(parts == 1 || parts == 2, GR_E_INVALID, "parts must be 1 or 2");
+  GR_REQUIRE(elem_type == GR_ELEM_BF16 || elem_type == GR_ELEM_FP16, GR_E_INVALID, "unknown element type");
+  if (n == 0) return GR_OK;
+  GR_REQUIRE(x && out_q, GR_E_INVALID, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)gr::sm_count() * 16);
+  score_prep_kernel<<<grid, 256, 0, st>>>(x, n, d, center_or_null, d_pad, parts, elem_type, out_q, stats_or_null);
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}
+
+extern "C" int gr_rescore_topk_f32(const float* h_user, const float* h_item, int64_t item_id_base, int32_t d,
+                                   const float* center_or_null, const float* sl_score, const int32_t* sl_id,
+                                   int32_t shortlist, int64_t n_users, const float* stats, float err_rel,
+                                   float err_abs, float tie_tol, int32_t k, float eps, int32_t* out_ids,
+                                   float* out_scores, int32_t* overflow_users, int32_t* n_overflow,
+                                   gr_stream_t stream) {
+  GR_REQUIRE(n_users >= 0 && d > 0 && d <= 4096, GR_E_INVALID, "bad shape");
+  GR_REQUIRE(shortlist >= 1 && shortlist <= 32, GR_E_INVALID, "shortlist must be in [1, 32]");
+  GR_REQUIRE(k >= 1 && k <= 32, GR_E_INVALID, "k must be in [1, 32]");
+  if (n_users == 0) return GR_OK;
+  GR_REQUIRE(h_user && h_item && sl_score && sl_id && stats && out_ids && out_scores && overflow_users && n_overflow,
+             GR_E_INVALID, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<int64_t>((n_users + RS_WARPS - 1) / RS_WARPS, (int64_t)gr::sm_count() * 8);
+  const size_t smem = sizeof(float) * RS_WARPS * d;
+  if (smem > 48 * 1024) GR_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rescore_kernel<<<grid, RS_WARPS * 32, smem, st>>>(h_user, h_item, item_id_base, d, center_or_null, sl_score, sl_id,
+                                                    shortlist, n_users, stats, err_rel, err_abs, tie_tol, k, eps,
+                                                    out_ids, out_scores, overflow_users, n_overflow);
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}
+
+extern "C" int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_list_or_null,
+                                       const int32_t* n_list_or_null, int64_t n_users, const float* h_item,
+                                       int64_t n_items, int64_t item_id_base, int32_t d,
+                                       const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null,
+                                       int32_t k, float eps, int32_t* out_ids, float* out_scores, gr_stream_t stream) {
+  GR_REQUIRE(n_users >= 0 && n_items >= 0 && d > 0 && d <= 4096, GR_E_INVALID, "bad shape");
+  GR_REQUIRE(k >= 1 && k <= 32, GR_E_INVALID, "k must be in [1, 32]");
+  GR_REQUIRE(item_id_base >= 0 && item_id_base + n_items <= 0x7fffffffLL, GR_E_INVALID, "item ids must fit int32");
+  if (n_users == 0) return GR_OK;
+  GR_REQUIRE(h_user && out_ids && out_scores && (n_items == 0 || h_item), GR_E_INVALID, "null pointer");
+  GR_REQUIRE(bought_indptr_or_null == nullptr || bought_ids_or_null != nullptr, GR_E_INVALID,
+             "bought_indptr without bought_ids");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(float) * ((d + 3) & ~3) + (size_t)k * EX_THREADS * 8;
+  GR_CUDA(cudaFuncSetAttribute(exact_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(n_users, (int64_t)gr::sm_count() * 8);
+  exact_topk_kernel<<<grid, EX_THREADS, smem, st>>>(
+      h_user, user_list_or_null, n_list_or_null, n_users, h_item, n_items, item_id_base, d,
+      reinterpret_cast<const long long*>(bought_indptr_or_null), bought_ids_or_null, k, eps, out_ids, out_scores);
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}
+
+extern "C" int gr_topk_merge(const float* scores, const int32_t* ids, int32_t parts, int64_t n_users, int32_t k_in,
+                             int32_t k_out, float* out_scores, int32_t* out_ids, gr_stream_t stream) {
+  GR_REQUIRE(parts >= 1 && parts <= 32, GR_E_INVALID, "parts must be in [1, 32]");
+  GR_REQUIRE(n_users >= 0 && k_in >= 1 && k_out >= 1, GR_E_INVALID, "bad shape");
+  if (n_users == 0) return GR_OK;
+  GR_REQUIRE(scores && ids && out_scores && out_ids, GR_E_INVALID, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<int64_t>((n_users + 7) / 8, (int64_t)gr::sm_count() * 16);
+  topk_merge_kernel<<<grid, 256, 0, st>>>(scores, ids, parts, n_users, k_in, k_out, out_scores, out_ids);
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}

@@ -240,6 +240,8 @@ class HeteroGraph:
         self._node_frames = {t: {} for t in self._num}
         self._edge_frames = {c: {} for c in self._edges}
         self._csr_cache: Dict[CEType, Tuple[np.ndarray, np.ndarray, np.ndarray]] = {}
+        self._dev_blocks: Dict = {}
+        self._dev_edges: Dict = {}
 
     # ---- metagraph ----
     @property
@@ -351,6 +353,27 @@ class HeteroGraph:
         sf = {t: dict(frames[t], **{NID: ids[t]}) for t in self._num}
         df = {t: dict(frames[t], **{NID: ids[t]}) for t in self._num}
         return Block(rels, self._num, self._num, sf, df)
+
+    def full_block_on(self, device, edge_weight: Optional[str] = None) -> Block:
+        """Device-resident full-graph block, built once per (device, edge weight) and kept: the graph structure
+        stays in HBM across ``get_embeddings`` calls instead of being re-sent per batch (``run.py:338-339``).
+        Node features are NOT cached here -- they travel with each call."""
+        key = (str(device), edge_weight)
+        if key not in self._dev_blocks:
+            self._dev_blocks[key] = self.full_block(edge_weight, with_features=False).to(device)
+        return self._dev_blocks[key]
+
+    def device_edges(self, etype, device):
+        """(src, dst) of one relation as int32 device tensors (cached) -- what the edge-scoring kernel reads."""
+        c = self.to_canonical_etype(etype)
+        key = (c, str(device))
+        if key not in self._dev_edges:
+            s, d = self._edges[c]
+            if s.size and (int(s.max()) > INT32_MAX or int(d.max()) > INT32_MAX):
+                raise OverflowError('node ids exceed int32')
+            self._dev_edges[key] = (torch.from_numpy(s.astype(np.int32)).to(device),
+                                    torch.from_numpy(d.astype(np.int32)).to(device))
+        return self._dev_edges[key]
 
     def to(self, device, **kwargs):
         return self  # structure stays on the host; blocks carry the device-resident CSR

@@ -1,0 +1,180 @@
+"""Thin Python wrappers over the C ABI: one function per entry point, tensors in / tensors out.
+
+Everything here runs on the current CUDA device and stream; inputs must be contiguous CUDA tensors (fp32
+features, int32 CSR). No CPU path exists -- see ``_native.py``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_ws_cache = {}
+
+
+def _ws(nbytes: int, device, tag: str) -> torch.Tensor:
+    """Per-(device, tag) grow-only scratch buffer (the library never allocates)."""
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = N.workspace(nbytes, device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """``y = x @ wt (+ bias) (relu)`` with ``wt`` = ``nn.Linear.weight.t()`` ([d_in, d_out], contiguous)."""
+    x, wt = _f32(x), _f32(wt)
+    n, d_in = x.shape
+    d_out = wt.shape[1]
+    assert wt.shape[0] == d_in
+    y = torch.empty((n, d_out), dtype=torch.float32, device=x.device)
+    N.call('gr_linear_f32', N.ptr(x), n, d_in, N.ptr(wt), N.ptr(_f32(bias)) if bias is not None else None, d_out,
+           int(relu), N.ptr(y), N.stream())
+    return y
+
+
+def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, out, reducer: int, l2norm: bool,
+                  accumulate: int = N.ACC_STORE, z_scale: float = 1.0, row_begin: int = 0, row_end: Optional[int] = None):
+    """Fused ``ConvLayer.forward`` of one relation into ``out[row_begin:row_end]`` (see include/gnn_recsys_b200.h)."""
+    nnz = int(indices.shape[0])
+    n_dst = int(indptr.shape[0]) - 1
+    row_end = n_dst if row_end is None else row_end
+    d_neigh, d_self, d_out = h_src.shape[1], h_dst.shape[1], w_self_t.shape[1]
+    assert w_self_t.shape[0] == d_self and w_neigh_t.shape[0] == d_neigh and w_neigh_t.shape[1] == d_out
+    assert out.shape[1] == d_out and indptr.dtype == torch.int32 and indices.dtype == torch.int32
+    lib = N.load()
+    nb = lib.gr_sage_relation_workspace_bytes(nnz, d_neigh)
+    ws = _ws(nb, out.device, 'sage')
+    N.call('gr_sage_relation_f32', N.ptr(indptr), N.ptr(indices), N.ptr(edge_w) if edge_w is not None else None, nnz,
+           N.ptr(h_src), N.ptr(h_dst), row_begin, row_end, d_neigh, d_self, N.ptr(w_self_t), N.ptr(w_neigh_t), d_out,
+           reducer, int(l2norm), accumulate, float(z_scale), N.ptr(out), N.ptr(ws), ws.numel(), N.stream())
+    return out
+
+
+def gather_reduce(indptr, indices, edge_w, h_src, reducer: int, row_begin: int = 0, row_end: Optional[int] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nnz = int(indices.shape[0])
+    n_dst = int(indptr.shape[0]) - 1
+    row_end = n_dst if row_end is None else row_end
+    d = h_src.shape[1]
+    if out is None:
+        out = torch.zeros((n_dst, d), dtype=torch.float32, device=h_src.device)
+    lib = N.load()
+    ws = _ws(lib.gr_sage_relation_workspace_bytes(nnz, d), h_src.device, 'sage')
+    N.call('gr_gather_reduce_f32', N.ptr(indptr), N.ptr(indices), N.ptr(edge_w) if edge_w is not None else None, nnz,
+           N.ptr(h_src), row_begin, row_end, d, reducer, N.ptr(out), N.ptr(ws), ws.numel(), N.stream())
+    return out
+
+
+def edge_cosine(u: torch.Tensor, v: torch.Tensor, h_src: torch.Tensor, h_dst: torch.Tensor) -> torch.Tensor:
+    """Cosine of ``h_src[u[e]]`` and ``h_dst[v[e]]`` for every edge; returns ``[E, 1]`` like ``edata['cos']``."""
+    e = int(u.shape[0])
+    out = torch.empty((e, 1), dtype=torch.float32, device=h_src.device)
+    assert u.dtype == torch.int32 and v.dtype == torch.int32 and h_src.shape[1] == h_dst.shape[1]
+    N.call('gr_edge_cosine_f32', N.ptr(u), N.ptr(v), e, N.ptr(h_src), N.ptr(h_dst), h_src.shape[1], N.ptr(out),
+           N.stream())
+    return out
+
+
+def colmean_normalized(x: torch.Tensor) -> torch.Tensor:
+    n, d = x.shape
+    center = torch.empty(d, dtype=torch.float32, device=x.device)
+    lib = N.load()
+    ws = _ws(lib.gr_colmean_workspace_bytes(n, d), x.device, 'colmean')
+    N.call('gr_colmean_normalized_f32', N.ptr(x), n, d, N.ptr(center), N.ptr(ws), ws.numel(), N.stream())
+    return center
+
+
+def score_prep(x: torch.Tensor, center: Optional[torch.Tensor], d_pad: int, parts: int, elem_type: int,
+               want_stats: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Quantised operand rows ``[n, parts * d_pad]`` (int16 storage) and ``stats = [max |row - center|, min |row|]``."""
+    n, d = x.shape
+    q = torch.empty((n, parts * d_pad), dtype=torch.int16, device=x.device)
+    stats = None
+    if want_stats:
+        stats = torch.tensor([0.0, float('inf')], dtype=torch.float32, device=x.device)
+    N.call('gr_score_prep', N.ptr(x), n, d, N.ptr(center) if center is not None else None, d_pad, parts, elem_type,
+           N.ptr(q), N.ptr(stats) if stats is not None else None, N.stream())
+    return q, stats
+
+
+def score_topk_tc(users_q, items_q, item_id_base: int, d_pad: int, parts: int, elem_type: int, bought_indptr,
+                  bought_ids, shortlist: int):
+    n_users, n_items = users_q.shape[0], items_q.shape[0]
+    dev = users_q.device
+    sl_score = torch.empty((n_users, shortlist), dtype=torch.float32, device=dev)
+    sl_id = torch.empty((n_users, shortlist), dtype=torch.int32, device=dev)
+    lib = N.load()
+    ws = _ws(lib.gr_score_topk_workspace_bytes(n_users, n_items, shortlist), dev, 'score')
+    N.call('gr_score_topk_tc', N.ptr(users_q), n_users, N.ptr(items_q), n_items, item_id_base, d_pad, parts, elem_type,
+           N.ptr(bought_indptr) if bought_indptr is not None else None,
+           N.ptr(bought_ids) if bought_ids is not None else None, shortlist, N.ptr(sl_score), N.ptr(sl_id), N.ptr(ws),
+           ws.numel(), N.stream())
+    return sl_score, sl_id
+
+
+def rescore_topk(h_user, h_item, item_id_base: int, center, sl_score, sl_id, stats, err_rel: float, err_abs: float,
+                 tie_tol: float, k: int, eps: float):
+    n_users, d = h_user.shape
+    dev = h_user.device
+    out_ids = torch.empty((n_users, k), dtype=torch.int32, device=dev)
+    out_scores = torch.empty((n_users, k), dtype=torch.float32, device=dev)
+    overflow = torch.empty(max(n_users, 1), dtype=torch.int32, device=dev)
+    n_overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    N.call('gr_rescore_topk_f32', N.ptr(h_user), N.ptr(h_item), item_id_base, d,
+           N.ptr(center) if center is not None else None, N.ptr(sl_score), N.ptr(sl_id), sl_id.shape[1], n_users,
+           N.ptr(stats), err_rel, err_abs, tie_tol, k, eps, N.ptr(out_ids), N.ptr(out_scores), N.ptr(overflow),
+           N.ptr(n_overflow), N.stream())
+    return out_ids, out_scores, overflow, n_overflow
+
+
+def score_topk_exact(h_user, h_item, item_id_base: int, bought_indptr, bought_ids, k: int, eps: float,
+                     user_list=None, n_list=None, out_ids=None, out_scores=None):
+    """Exact fp32 top-k for the listed users (all users when ``user_list`` is None), written in place into
+    ``out_ids`` / ``out_scores`` rows of those users."""
+    n_users, d = h_user.shape
+    dev = h_user.device
+    if out_ids is None:
+        out_ids = torch.full((n_users, k), -1, dtype=torch.int32, device=dev)
+        out_scores = torch.full((n_users, k), float('-inf'), dtype=torch.float32, device=dev)
+    N.call('gr_score_topk_exact_f32', N.ptr(h_user), N.ptr(user_list) if user_list is not None else None,
+           N.ptr(n_list) if n_list is not None else None, n_users, N.ptr(h_item), h_item.shape[0], item_id_base, d,
+           N.ptr(bought_indptr) if bought_indptr is not None else None,
+           N.ptr(bought_ids) if bought_ids is not None else None, k, eps, N.ptr(out_ids), N.ptr(out_scores),
+           N.stream())
+    return out_ids, out_scores
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
+    """``scores`` / ``ids``: ``[parts, n_users, k_in]`` -> ``[n_users, k_out]`` best by (score desc, id asc)."""
+    parts, n_users, k_in = scores.shape
+    dev = scores.device
+    out_s = torch.empty((n_users, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((n_users, k_out), dtype=torch.int32, device=dev)
+    N.call('gr_topk_merge', N.ptr(scores), N.ptr(ids), parts, n_users, k_in, k_out, N.ptr(out_s), N.ptr(out_i),
+           N.stream())
+    return out_s, out_i
+
+
+def csr_build(src: torch.Tensor, dst: torch.Tensor, n_dst: int):
+    """Stable COO -> CSR over destination rows on the device: ``(indptr, indices, eperm)``, all int32."""
+    assert src.dtype == torch.int32 and dst.dtype == torch.int32
+    nnz = int(src.shape[0])
+    dev = src.device
+    indptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    eperm = torch.empty(nnz, dtype=torch.int32, device=dev)
+    lib = N.load()
+    ws = N.workspace(lib.gr_csr_build_workspace_bytes(nnz, n_dst), dev)
+    N.call('gr_csr_build_i32', N.ptr(src), N.ptr(dst), nnz, n_dst, N.ptr(indptr), N.ptr(indices), N.ptr(eperm),
+           N.ptr(ws), ws.numel(), N.stream())
+    return indptr, indices, eperm

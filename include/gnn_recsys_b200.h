@@ -1,0 +1,136 @@
+/*
+ * gnn_recsys_b200.h -- C ABI of the B200 (sm_100a) embedding + recommendation hot path of hieucnm/GNN-RecSys.
+ *
+ * The reference has no FFI: its seam is the Python API of src/model.py, src/train/run.py::get_embeddings and
+ * src/metrics.py::get_recs sitting on dgl==0.5.2 / torch==1.6 library calls. Each entry point below replaces
+ * the library call(s) named in its comment (paths relative to the reference repository root); the Python
+ * mirror in gnn-recsys_b200/ binds them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the caller owns all buffers, including scratch ("ws") sized by the matching *_workspace_bytes query
+ *   - the library never allocates or frees device memory, never synchronises, never changes the device
+ *   - work is enqueued on `stream` (a cudaStream_t); pass 0/NULL for the legacy default stream
+ *   - return value: 0 = ok, negative = error (GR_E_*); gr_last_error() returns a thread-local message
+ *   - row-major fp32 feature matrices with leading dimension == number of columns; int32 CSR
+ */
+#ifndef GNN_RECSYS_B200_H_
+#define GNN_RECSYS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gr_stream_t; /* cudaStream_t */
+
+enum {
+  GR_OK = 0,
+  GR_E_INVALID = -1,     /* bad argument (null pointer, unsupported dimension, ...) */
+  GR_E_WORKSPACE = -2,   /* workspace too small */
+  GR_E_CUDA = -3,        /* a CUDA call or kernel launch failed */
+  GR_E_UNSUPPORTED = -4  /* valid request this build cannot serve (e.g. not an sm_100 device) */
+};
+
+enum { GR_REDUCE_MEAN = 0, GR_REDUCE_MAX = 1 };            /* fn.mean / fn.max, src/model.py:145-161 */
+enum { GR_ACC_STORE = 0, GR_ACC_ADD = 1, GR_ACC_MAX = 2 }; /* HeteroGraphConv aggregate, src/model.py:384-406 */
+
+const char* gr_last_error(void);
+int gr_version(void);
+/* sm count / compute capability of the current device; GR_E_UNSUPPORTED unless it is sm_100. */
+int gr_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---- a1 NodeEmbedding.forward (src/model.py:19-24, nn.Linear with bias) and the pre-aggregation projection
+ *      relu(fc_preagg(h)) of mean_nn / pool_nn (src/model.py:151,158; bias-free). Replaces torch addmm / cuBLAS sgemm.
+ *      y[n, d_out] = x[n, d_in] . wt[d_in, d_out] (+ bias) (relu).  `wt` is the nn.Linear weight TRANSPOSED
+ *      (k-major) so that output columns are contiguous.  fp32 FFMA accumulation in k order. */
+int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const float* wt, const float* bias_or_null,
+                  int32_t d_out, int relu, float* y, gr_stream_t stream);
+
+/* ---- a3-a6 ConvLayer.forward for one relation, fused (src/model.py:123-237), replacing DGL update_all
+ *      (libdgl SpMM copy_u/u_mul_e + mean/max), two torch sgemm, relu, norm/where/div and HeteroGraphConv's
+ *      stack+reduce:
+ *        n_v   = reduce_{e: dst(e)=v} (edge_w[e] *) h_src[indices[e]]       mean: sum / max(deg,1); max: 0 if deg==0
+ *        z_v   = relu(h_dst[v] . w_self_t + n_v . w_neigh_t);  z_v /= (|z_v| or 1 if 0)   when l2norm
+ *        out_v = z_scale * ( z_v (GR_ACC_STORE) | out_v + z_v (GR_ACC_ADD) | max(out_v, z_v) (GR_ACC_MAX) )
+ *      (HeteroGraphConv 'mean' = ADD with z_scale = 1/n on the last relation, like stack(...).mean(0))
+ *      for destination rows v in [row_begin, row_end) (a contiguous shard; out / h_dst are indexed by v).
+ *      indptr has n_dst+1 entries and indexes `indices` / `edge_w` absolutely; nnz = indptr[n_dst].
+ *      Rows with more than GR_SAGE_LONG_ROW in-edges are reduced by a deterministic multi-CTA split. */
+#define GR_SAGE_LONG_ROW 2048
+#define GR_SAGE_CHUNK 2048
+size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh);
+int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indices, const float* edge_w_or_null, int64_t nnz,
+                         const float* h_src, const float* h_dst, int64_t row_begin, int64_t row_end,
+                         int32_t d_neigh, int32_t d_self, const float* w_self_t, const float* w_neigh_t,
+                         int32_t d_out, int reducer, int l2norm, int accumulate, float z_scale, float* out,
+                         void* ws, size_t ws_bytes, gr_stream_t stream);
+
+/* The gather-reduce alone (no projection): agg[v - row_begin... indexed by v] = reduce of neighbour rows. Used to
+ * report aggregation bandwidth in isolation and by tests; same kernels as above without the epilogue. */
+int gr_gather_reduce_f32(const int32_t* indptr, const int32_t* indices, const float* edge_w_or_null, int64_t nnz,
+                         const float* h_src, int64_t row_begin, int64_t row_end, int32_t d, int reducer,
+                         float* agg, void* ws, size_t ws_bytes, gr_stream_t stream);
+
+/* ---- a10 CosinePrediction.forward for one etype (src/model.py:317-327): replaces F.normalize x2 + DGL SDDMM u_dot_v.
+ *      out[e] = <h_src[u[e]], h_dst[v[e]]> / (max(|h_src[u[e]]|, 1e-12) * max(|h_dst[v[e]]|, 1e-12)) */
+int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, const float* h_src, const float* h_dst,
+                       int32_t d, float* out, gr_stream_t stream);
+
+/* ---- a13 get_recs (src/metrics.py:52-77): all users x all items cosine + top-k, replacing the per-user
+ *      torch.cat / nn.CosineSimilarity / np.argsort / Python filter loop.
+ *
+ *  stage 0  gr_score_prep: rows are L2-normalised (x / max(|x|, 1e-12)), optionally shifted by `center`
+ *           (the ranking per user is invariant to a common item shift; it shrinks the quantisation error bound),
+ *           zero-padded to d_pad (64 or 128) and rounded to 16 bit (GR_ELEM_BF16 | GR_ELEM_FP16). parts == 2 stores a
+ *           hi and a lo half per row ([hi d_pad | lo d_pad], x = hi + lo up to 2^-18 / 2^-22 relative) for the
+ *           3-product scheme hi.hi + lo.hi + hi.lo. stats[0] (caller-initialised 0) receives max_i |row_i - center|
+ *           (atomic max) and stats[1] (caller-initialised +inf) the smallest non-zero |x_i| (atomic min); the
+ *           first bounds the scoring error, the second tells stage 2 when the eps clamp of the cosine can bind.
+ *           gr_colmean_normalized_f32 computes a deterministic `center` (mean of the normalised rows).
+ *  stage 1  gr_score_topk_tc: TMA-fed tcgen05 GEMM users x items^T (16-bit in, fp32 accumulate in TMEM) with a
+ *           fused per-user running top-`shortlist` epilogue that skips already-bought items. Bought lists are a CSR
+ *           per user (int64 indptr, int32 ids sorted ascending, GLOBAL item ids, duplicates allowed). Output: per
+ *           user the `shortlist` best approximate (centred) scores, descending, and their global item ids (-1 = empty
+ *           slot).
+ *  stage 2  gr_rescore_topk_f32: exact fp32 cosine (torch formula x.y / sqrt(max(|x|^2 |y|^2, eps^2))) of the
+ *           shortlisted items, sorted by (score desc, id asc), first k. Proves per user that no item outside the
+ *           shortlist can enter the top-k by more than tie_tol: with tau = the shortlist's last approximate score and
+ *           err = err_rel * stats[0] + err_abs, every outside item scores <= tau + err (+ x.center) exactly; users for
+ *           which kth_exact < that bound - tie_tol are appended to overflow_users / n_overflow (caller zero-initialises
+ *           n_overflow) and must be recomputed by stage 3.
+ *  stage 3  gr_score_topk_exact_f32: exact fp32 scoring of all items for the listed users (the overflow list, or
+ *           every user when user_list == NULL): the always-correct fallback and the brute-force checker.
+ *  merge    gr_topk_merge: row-wise merge of `parts` partial (score desc, id) lists into the k_out best
+ *           (scores[p][u][k_in]); ties by smaller id; ids < 0 are empty slots. */
+enum { GR_ELEM_BF16 = 0, GR_ELEM_FP16 = 1 };
+#define GR_SCORE_MAX_SPLITS 32
+size_t gr_colmean_workspace_bytes(int64_t n, int32_t d);
+int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, float* center, void* ws, size_t ws_bytes,
+                              gr_stream_t stream);
+int gr_score_prep(const float* x, int64_t n, int32_t d, const float* center_or_null, int32_t d_pad, int32_t parts,
+                  int32_t elem_type, uint16_t* out_q, float* stats_or_null, gr_stream_t stream);
+int gr_score_splits(int64_t n_users, int64_t n_items);
+size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t shortlist);
+int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const uint16_t* items_q, int64_t n_items,
+                     int64_t item_id_base, int32_t d_pad, int32_t parts, int32_t elem_type,
+                     const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t shortlist,
+                     float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes, gr_stream_t stream);
+int gr_rescore_topk_f32(const float* h_user, const float* h_item, int64_t item_id_base, int32_t d,
+                        const float* center_or_null, const float* sl_score, const int32_t* sl_id, int32_t shortlist,
+                        int64_t n_users, const float* stats, float err_rel, float err_abs, float tie_tol, int32_t k,
+                        float eps, int32_t* out_ids, float* out_scores, int32_t* overflow_users, int32_t* n_overflow,
+                        gr_stream_t stream);
+int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_list_or_null, const int32_t* n_list_or_null,
+                            int64_t n_users, const float* h_item, int64_t n_items, int64_t item_id_base, int32_t d,
+                            const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t k,
+                            float eps, int32_t* out_ids, float* out_scores, gr_stream_t stream);
+int gr_topk_merge(const float* scores, const int32_t* ids, int32_t parts, int64_t n_users, int32_t k_in,
+                  int32_t k_out, float* out_scores, int32_t* out_ids, gr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNN_RECSYS_B200_H_ */

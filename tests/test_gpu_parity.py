@@ -1,0 +1,340 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures written by the reference's own code
+and against the CPU oracle on seeded inputs. Tolerances are the north_star's: embeddings rtol 1e-4 / atol 1e-5
+(fp32), top-k ids identical except where the fp32 score gap is under 1e-5, CSR bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (EMBED_CASES, RELS, load_case, state_dict, case_relations, case_occurrence,
+                     assert_topk_equivalent)
+from oracle import straightline as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-5
+
+
+@pytest.fixture(scope='module')
+def grb():
+    import gnn_recsys_b200 as m
+    m._native.load()
+    assert torch.cuda.is_available()
+    return m
+
+
+def product_graph(grb, meta, z):
+    g = grb.HeteroGraph({c: (s, d) for c, (s, d) in case_relations(z).items()},
+                        {'user': meta['n_users'], 'item': meta['n_items']})
+    g.nodes['user'].data['features'] = torch.from_numpy(z['user_feat'])
+    g.nodes['item'].data['features'] = torch.from_numpy(z['item_feat'])
+    for c, occ in case_occurrence(z).items():
+        g.edges[c].data['occurrence'] = torch.from_numpy(occ)
+    return g
+
+
+def product_model(grb, g, meta, z, dev):
+    model = grb.ConvModel(g, meta['n_layers'], {'user': 2, 'item': 4, 'hidden': meta['hidden'], 'out': meta['out']},
+                          meta['norm'], 0.0, meta['aggregator'], 'cos', meta['hetero'], meta['embedding_layer'])
+    missing = model.load_state_dict(state_dict(z), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.to(dev).eval()
+
+
+@pytest.mark.parametrize('name', EMBED_CASES)
+def test_embeddings_match_reference(grb, name):
+    meta, z = load_case(name)
+    dev = torch.device('cuda:0')
+    g = product_graph(grb, meta, z)
+    model = product_model(grb, g, meta, z, dev)
+    conv = meta['n_layers'] - 1 if meta['embedding_layer'] else meta['n_layers']
+    nids = {'user': z['user_ids'], 'item': np.arange(meta['n_items'])}
+    ew = 'occurrence' if meta['aggregator'].endswith('_edge') else None
+    loader = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(conv), batch_size=None, edge_weight=ew)
+    y = grb.get_embeddings(g, meta['out'], model, loader, len(loader), True, dev, meta['embedding_layer'])
+    for t in ('user', 'item'):
+        assert y[t].is_cuda and tuple(y[t].shape) == z['emb/' + t].shape
+        np.testing.assert_allclose(y[t].cpu().numpy(), z['emb/' + t], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize('name', ['tiny_mean_batched', 'tiny_pool_nn', 'small_mean_128'])
+def test_embeddings_minibatch_loader(grb, name):
+    """The reference's own batching (128-node shuffled mini-batches of sampled blocks) through the same kernels."""
+    meta, z = load_case(name)
+    dev = torch.device('cuda:0')
+    g = product_graph(grb, meta, z)
+    model = product_model(grb, g, meta, z, dev)
+    conv = meta['n_layers'] - 1 if meta['embedding_layer'] else meta['n_layers']
+    nids = {'user': z['user_ids'], 'item': np.arange(meta['n_items'])}
+    loader = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(conv), batch_size=32, shuffle=True, seed=5)
+    y = grb.get_embeddings(g, meta['out'], model, loader, len(loader), False, dev, meta['embedding_layer'])
+    for t in ('user', 'item'):
+        assert not y[t].is_cuda
+        np.testing.assert_allclose(y[t].numpy(), z['emb/' + t], rtol=RTOL, atol=ATOL)
+
+
+RECS_CONFIGS = [dict(elem='bf16', parts=2), dict(elem='fp16', parts=2), dict(elem='bf16', parts=1),
+                dict(elem='fp16', parts=1, center=False), dict(exact_only=True), dict(elem='bf16', parts=2, tie_tol=0.0)]
+
+
+@pytest.mark.parametrize('cfg', RECS_CONFIGS, ids=lambda c: '-'.join('%s=%s' % kv for kv in c.items()))
+@pytest.mark.parametrize('name', ['tiny_mean', 'tiny_pool_nn', 'tiny_mean_nonorm', 'small_mean_128', 'small_pool_256'])
+def test_recs_match_reference(grb, name, cfg):
+    meta, z = load_case(name)
+    dev = torch.device('cuda:0')
+    g = product_graph(grb, meta, z)
+    h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    buys = case_relations(z)[('user', 'buys', 'item')]
+    uids = z['user_ids'].tolist()
+    scores = O.get_recs_scores(h['user'], h['item'], uids).numpy()
+    bought = grb.BoughtCSR.from_edges(buys[0], buys[1], meta['n_users'])
+    ids = grb.get_recs_tensor(g, h, meta['k'], uids, bought, True, dev, config=grb.RecsConfig(**cfg))
+    assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), z['recs'], scores, meta['k'])
+    keep = grb.get_recs_tensor(g, h, meta['k'], uids[:8], None, False, dev, config=grb.RecsConfig(**cfg))
+    assert_topk_equivalent(keep.cpu().numpy().astype(np.int64), z['recs_keep'], scores[:8], meta['k'])
+
+
+def test_get_recs_dict_api(grb):
+    """Reference call shape: dict in, dict of lists out (src/metrics.py:31-78, main_inference.py:143-166)."""
+    meta, z = load_case('tiny_mean')
+    g = product_graph(grb, meta, z)
+    h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    uids = z['user_ids'].tolist()
+    bought_eids = g.out_edges(u=torch.tensor(uids), form='eid', etype='buys')
+    bought = grb.create_already_bought(g, bought_eids)
+    recs = grb.get_recs(g, h, None, meta['out'], meta['k'], uids, bought, remove_already_bought=True, cuda=True,
+                        device=torch.device('cuda:0'), pred='cos', use_popularity=False)
+    assert set(recs.keys()) == set(uids) and all(isinstance(v, list) for v in recs.values())
+    got = np.full((len(uids), meta['k']), -1, dtype=np.int64)
+    for r, u in enumerate(uids):
+        got[r, :len(recs[u])] = recs[u]
+    scores = O.get_recs_scores(h['user'], h['item'], uids).numpy()
+    assert_topk_equivalent(got, z['recs'], scores, meta['k'])
+    for u in uids:
+        assert not set(recs[u]) & set(bought[u])
+    with pytest.raises(KeyError):
+        grb.get_recs(g, h, None, meta['out'], meta['k'], uids, bought, pred='dot')
+    same = grb.get_recs(g, h, None, meta['out'], meta['k'], uids, grb.create_already_bought_csr(g, bought_eids))
+    assert all(list(same[u]) == list(recs[u]) for u in uids)
+
+
+def test_forward_scores_and_loss_match_reference(grb):
+    meta, z = load_case('fwd_fanout_mean')
+    dev = torch.device('cuda:0')
+    blocks = []
+    for li in range(meta['n_blocks']):
+        ns = {t: int(z['block%d/nsrc/%s' % (li, t)]) for t in ('user', 'item')}
+        nd = {t: int(z['block%d/ndst/%s' % (li, t)]) for t in ('user', 'item')}
+        rels = {}
+        for c in RELS:
+            rels[c] = grb.Relation(torch.from_numpy(z['block%d/indptr/%s' % (li, c[1])].astype(np.int32)),
+                                   torch.from_numpy(z['block%d/indices/%s' % (li, c[1])].astype(np.int32)),
+                                   ns[c[0]], nd[c[2]])
+        blocks.append(grb.Block(rels, ns, nd).to(dev))
+    sizes = blocks[-1].num_dst
+    pos_g = grb.edge_graph(sizes, {c: (z['pos/%s/src' % c[1]], z['pos/%s/dst' % c[1]]) for c in RELS})
+    neg_g = grb.edge_graph(sizes, {c: (z['neg/%s/src' % c[1]], z['neg/%s/dst' % c[1]]) for c in RELS})
+    stub = grb.HeteroGraph({c: (np.zeros(0, np.int64), np.zeros(0, np.int64)) for c in RELS}, {'user': 1, 'item': 1})
+    model = grb.ConvModel(stub, meta['n_layers'], {'user': 2, 'item': 4, 'hidden': meta['hidden'], 'out': meta['out']},
+                          True, 0.0, meta['aggregator'], 'cos', 'sum', True)
+    model.load_state_dict(state_dict(z))
+    model = model.to(dev).eval()
+    feats = {t: torch.from_numpy(z['feat/' + t]) for t in ('user', 'item')}
+    h, pos, neg = model(blocks, feats, pos_g, neg_g, True)
+    assert feats['user'].shape[1] == meta['hidden']  # embedded in place in the caller's dict, like the reference
+    for t in ('user', 'item'):
+        np.testing.assert_allclose(h[t].cpu().numpy(), z['h/' + t], rtol=RTOL, atol=ATOL)
+    for c in RELS:
+        assert tuple(pos[c].shape) == z['pos/%s/score' % c[1]].shape
+        np.testing.assert_allclose(pos[c].cpu().numpy(), z['pos/%s/score' % c[1]], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(neg[c].cpu().numpy(), z['neg/%s/score' % c[1]], rtol=RTOL, atol=ATOL)
+    loss = grb.max_margin_loss(pos, neg, meta['delta'], meta['neg_k'], cuda=True, device=dev)
+    np.testing.assert_allclose(float(loss), float(z['loss']), rtol=1e-5)
+
+
+def test_unknown_options_raise(grb):
+    g = grb.HeteroGraph({c: (np.zeros(0, np.int64), np.zeros(0, np.int64)) for c in RELS}, {'user': 1, 'item': 1})
+    dims = {'user': 2, 'item': 4, 'hidden': 8, 'out': 8}
+    with pytest.raises(KeyError):
+        grb.ConvModel(g, 2, dims, pred='bilinear')
+    m = grb.ConvModel(g, 2, dims, aggregator_type='median').cuda()
+    blk = grb.Block({RELS[0]: grb.Relation(torch.tensor([0, 1], dtype=torch.int32), torch.tensor([0], dtype=torch.int32),
+                                           1, 1)}, {'user': 1, 'item': 1}, {'user': 1, 'item': 1}).to('cuda')
+    with pytest.raises(KeyError):
+        m.get_repr([blk], {'user': torch.zeros(1, 8, device='cuda'), 'item': torch.zeros(1, 8, device='cuda')})
+
+
+# ------------------------------------------------------------------------------------------------ kernels vs oracle
+def random_csr(rng, n_src, n_dst, nnz, hub=None):
+    dst = rng.integers(0, n_dst, nnz)
+    if hub is not None:
+        dst[:hub] = 1  # one very long row
+    src = rng.integers(0, n_src, nnz)
+    indptr, indices, eperm = O.csr_by_dst(src, dst, n_dst)
+    return src, dst, indptr, indices, eperm
+
+
+@pytest.mark.parametrize('d', [128, 256, 64, 20])
+@pytest.mark.parametrize('reducer', ['mean', 'max'])
+def test_gather_reduce_vs_oracle(grb, d, reducer):
+    rng = np.random.default_rng(d)
+    n_src, n_dst, nnz = 3000, 1500, 40000
+    src, dst, indptr, indices, eperm = random_csr(rng, n_src, n_dst, nnz, hub=9000)  # hub row > GR_SAGE_LONG_ROW
+    x = torch.from_numpy(rng.standard_normal((n_src, d)).astype(np.float32))
+    w = torch.from_numpy(rng.integers(1, 5, nnz).astype(np.float32))
+    dev = 'cuda:0'
+    for use_w in (False, True):
+        want = O.neighbour_reduce(torch.from_numpy(src), torch.from_numpy(dst), w if use_w else None, x, n_dst, reducer)
+        wcsr = w[torch.from_numpy(eperm.astype(np.int64))].contiguous().to(dev) if use_w else None
+        got = grb.ops.gather_reduce(torch.from_numpy(indptr).to(dev), torch.from_numpy(indices).to(dev), wcsr,
+                                    x.to(dev), 1 if reducer == 'max' else 0)
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize('dims', [(128, 128, 128), (256, 256, 256), (256, 256, 128), (128, 128, 64), (4, 2, 16), (100, 60, 36)])
+@pytest.mark.parametrize('agg', ['mean', 'pool_nn'])
+def test_sage_relation_vs_oracle(grb, dims, agg):
+    dn, ds, dout = dims
+    rng = np.random.default_rng(dn + dout)
+    n_src, n_dst, nnz = 2000, 1111, 30000
+    src, dst, indptr, indices, eperm = random_csr(rng, n_src, n_dst, nnz, hub=5000)
+    dst[dst == 7] = 8  # an isolated destination row
+    indptr, indices, eperm = O.csr_by_dst(src, dst, n_dst)
+    hs = torch.from_numpy(np.abs(rng.standard_normal((n_src, dn))).astype(np.float32))
+    hd = torch.from_numpy(rng.standard_normal((n_dst, ds)).astype(np.float32))
+    hd[3] = 0
+    ws = torch.from_numpy((rng.standard_normal((dout, ds)) / np.sqrt(ds)).astype(np.float32))
+    wn = torch.from_numpy((rng.standard_normal((dout, dn)) / np.sqrt(dn)).astype(np.float32))
+    dev = 'cuda:0'
+    want = O.conv_layer(torch.from_numpy(src), torch.from_numpy(dst), None, hs, hd, ws, wn, None, 'mean', True)
+    if agg == 'pool_nn':
+        want = O.conv_layer(torch.from_numpy(src), torch.from_numpy(dst), None, hs, hd, ws, wn, torch.eye(dn), 'pool_nn', True)
+    out = torch.empty(n_dst, dout, device=dev)
+    red = 1 if agg == 'pool_nn' else 0
+    args = (torch.from_numpy(indptr).to(dev), torch.from_numpy(indices).to(dev), None, hs.to(dev), hd.to(dev),
+            ws.t().contiguous().to(dev), wn.t().contiguous().to(dev))
+    grb.ops.sage_relation(*args, out, red, True)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+    # accumulate modes and a destination shard
+    grb.ops.sage_relation(*args, out, red, True, grb._native.ACC_ADD, 0.5)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)  # (z + z) * 0.5
+    out2 = torch.full((n_dst, dout), -7.0, device=dev)
+    grb.ops.sage_relation(*args, out2, red, True, row_begin=100, row_end=900)
+    np.testing.assert_allclose(out2[100:900].cpu().numpy(), want[100:900].numpy(), rtol=RTOL, atol=ATOL)
+    assert bool((out2[:100] == -7).all()) and bool((out2[900:] == -7).all())
+
+
+@pytest.mark.parametrize('shape', [(1000, 2, 128), (777, 4, 256), (3000, 128, 128), (513, 256, 256), (100, 37, 19)])
+def test_linear_vs_torch(grb, shape):
+    n, din, dout = shape
+    g = torch.Generator().manual_seed(n)
+    x, w, b = torch.randn(n, din, generator=g), torch.randn(dout, din, generator=g), torch.randn(dout, generator=g)
+    for bias, relu in ((b, False), (None, True)):
+        want = x @ w.t() + (bias if bias is not None else 0)
+        want = torch.relu(want) if relu else want
+        got = grb.ops.linear(x.cuda(), w.t().contiguous().cuda(), None if bias is None else bias.cuda(), relu)
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL * (din ** 0.5))
+
+
+@pytest.mark.parametrize('d', [128, 256, 16, 33])
+def test_edge_cosine_vs_oracle(grb, d):
+    rng = np.random.default_rng(d)
+    hs = torch.from_numpy(rng.standard_normal((500, d)).astype(np.float32))
+    hd = torch.from_numpy(rng.standard_normal((300, d)).astype(np.float32))
+    hs[4] = 0
+    u, v = rng.integers(0, 500, 5000), rng.integers(0, 300, 5000)
+    u[:3] = 4
+    want = O.cosine_prediction({('a', 'r', 'b'): (u, v)}, {'a': hs, 'b': hd})[('a', 'r', 'b')]
+    got = grb.ops.edge_cosine(torch.from_numpy(u.astype(np.int32)).cuda(), torch.from_numpy(v.astype(np.int32)).cuda(),
+                              hs.cuda(), hd.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+    empty = grb.ops.edge_cosine(torch.zeros(0, dtype=torch.int32).cuda(), torch.zeros(0, dtype=torch.int32).cuda(),
+                                hs.cuda(), hd.cuda())
+    assert tuple(empty.shape) == (0, 1)
+
+
+@pytest.mark.parametrize('shape', [(5000, 700, 20000), (300000, 1 << 17, 1000000), (10, 5, 0), (70000, 1, 3000)])
+def test_csr_build_bit_exact(grb, shape):
+    n_src, n_dst, nnz = shape
+    rng = np.random.default_rng(nnz + 1)
+    src = rng.integers(0, n_src, nnz).astype(np.int32)
+    dst = (rng.zipf(1.3, nnz) % n_dst).astype(np.int32) if nnz else np.zeros(0, np.int32)
+    indptr, indices, eperm = grb.ops.csr_build(torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda(), n_dst)
+    w_indptr, w_indices, w_eperm = grb.csr_by_dst_host(src, dst, n_dst)
+    assert np.array_equal(indptr.cpu().numpy(), w_indptr)
+    assert np.array_equal(eperm.cpu().numpy(), w_eperm)
+    assert np.array_equal(indices.cpu().numpy(), w_indices)
+    if nnz and nnz <= 20000:  # the loop-based oracle restatement (slow) on the small case
+        o_indptr, o_indices, o_eperm = O.csr_by_dst(src, dst, n_dst)
+        assert np.array_equal(w_indptr, o_indptr) and np.array_equal(w_indices, o_indices) and np.array_equal(w_eperm, o_eperm)
+
+
+def test_topk_merge_vs_oracle(grb):
+    rng = np.random.default_rng(3)
+    parts, n, k_in, k_out = 5, 300, 16, 10
+    s = np.sort(rng.random((parts, n, k_in)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    ids = rng.permutation(parts * n * k_in).reshape(parts, n, k_in).astype(np.int32)
+    ids[:, :, -3:][rng.random((parts, n, 3)) < 0.5] = -1
+    s[ids < 0] = -np.inf
+    s = -np.sort(-s, axis=2)
+    order = np.argsort(-s, axis=2, kind='stable')
+    ids = np.take_along_axis(ids, order, 2)
+    ws, wi = O.merge_partial_topk([s[p] for p in range(parts)], [ids[p] for p in range(parts)], k_out)
+    gs, gi = grb.ops.topk_merge(torch.from_numpy(s).cuda(), torch.from_numpy(ids).cuda(), k_out)
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gs.cpu().numpy(), ws)
+
+
+# ------------------------------------------------------------------------------------------------ scoring at size
+def clustered_embeddings(rng, n, d, spread):
+    base = np.abs(rng.standard_normal(d)).astype(np.float32)
+    x = np.maximum(base[None, :] + spread * rng.standard_normal((n, d)).astype(np.float32), 0)
+    return torch.from_numpy(x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12))
+
+
+@pytest.mark.parametrize('cfg', [dict(elem='bf16', parts=2), dict(elem='fp16', parts=2), dict(elem='bf16', parts=1)],
+                         ids=['bf16x3', 'fp16x3', 'bf16x1'])
+def test_quantised_scores_within_error_bound(grb, cfg):
+    """The soundness proof of the shortlist rests on |approx - exact| <= err_rel * max|y - c| + err_abs: check it."""
+    rng = np.random.default_rng(11)
+    d, n_u, n_i = 128, 512, 4096
+    hu, hi = clustered_embeddings(rng, n_u, d, 0.3).cuda(), clustered_embeddings(rng, n_i, d, 0.3).cuda()
+    c = grb.RecsConfig(shortlist=32, **cfg)
+    table = grb.ScoringTable(hi, c)
+    users_q, _ = grb.ops.score_prep(hu, None, table.d_pad, c.parts, c.elem_type, False)
+    sl_s, sl_i = grb.ops.score_topk_tc(users_q, table.items_q, 0, table.d_pad, c.parts, c.elem_type, None, None, 32)
+    hu64, hi64 = hu.double().cpu(), hi.double().cpu()
+    center = table.center.double().cpu()
+    exact = hu64 @ (hi64 - center).t()
+    got = torch.gather(exact, 1, sl_i.long().cpu())
+    err = (got - sl_s.double().cpu()).abs().max().item()
+    bound = c.err_rel() * float(table.stats[0]) + c.err_abs(d)
+    assert err <= bound, (err, bound)
+    # and the shortlist really is the approximate top-32 (sorted, distinct)
+    assert bool((sl_s[:, :-1] >= sl_s[:, 1:]).all())
+    top = torch.topk(exact, 32, dim=1).values
+    assert float((top[:, -1] - got.min(1).values).max()) <= 2 * bound
+
+
+@pytest.mark.parametrize('shape', [(1000, 20000), (70000, 3000), (257, 129), (5, 40)])
+def test_recs_large_vs_exact_kernel_and_oracle(grb, shape):
+    """Tensor-core path == brute-force fp32 kernel == oracle (vectorised) on clustered embeddings with bought lists."""
+    n_u, n_i = shape
+    rng = np.random.default_rng(n_u)
+    d, k = 128, 10
+    hu, hi = clustered_embeddings(rng, n_u, d, 0.2), clustered_embeddings(rng, n_i, d, 0.2)
+    nb = rng.integers(0, 6, n_u)
+    bu = np.repeat(np.arange(n_u), nb)
+    bi = rng.integers(0, n_i, bu.size)
+    bought = grb.BoughtCSR.from_edges(bu, bi, n_u)
+    dev = 'cuda:0'
+    table = grb.ScoringTable(hi.to(dev), grb.RecsConfig())
+    ids, sc, n_over = grb.recommend_topk(hu.to(dev), table, k, bought, return_overflow=True)
+    ex_ids, ex_sc = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), grb.RecsConfig(exact_only=True)), k, bought)
+    sample = np.arange(n_u) if n_u <= 2000 else rng.choice(n_u, 2000, replace=False)
+    scores = O.get_recs_scores(hu, hi, sample).numpy()
+    assert_topk_equivalent(ids.cpu().numpy()[sample], ex_ids.cpu().numpy()[sample], scores, k)
+    want = O.get_recs_vectorised(hu, hi, k, sample, bought.indptr, bought.ids.astype(np.int64))
+    assert_topk_equivalent(ex_ids.cpu().numpy()[sample].astype(np.int64), want, scores, k)
+    assert_topk_equivalent(ids.cpu().numpy()[sample].astype(np.int64), want, scores, k)
+    for r in sample[:200]:
+        assert not set(ids[r].tolist()) & set(bought[r])
+    assert int(n_over) <= n_u
