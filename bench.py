@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: full-graph embeddings + top-10 recommendations for every user.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c5]
+
+One "step" = one pass of the hot path over the whole synthetic graph: NodeEmbedding -> ConvLayer stack over the
+four relations -> all-users x all-items cosine + top-10. Rank 0 prints ONE JSON line (see the keys at the bottom).
+
+  value      users/s with every input already resident in HBM (features, CSR), CUDA events, max over ranks
+  e2e        users/s through the public API (get_embeddings + get_recs_tensor) with HOST features (pinned), the
+             H2D copy of the features and the D2H copy of the [U, 10] id table inside the timed region
+  roofline   the dominant kernel (tcgen05 scoring GEMM) against the measured bf16 peak; roofline_aggregation: the
+             fused CSR gather-reduce kernels against the measured HBM bandwidth
+  cpu_baseline  the CPU oracle (reference semantics) on the box's host cores, bounded sample (rank 0, N = 1 only)
+
+--impl reference times the reference's own algorithm (oracle/straightline.py: the per-user get_recs loop of
+src/metrics.py:52-77 and the layer-wise CPU embedding pass) on the host cores. DGL 0.5.2 is not installable in this
+image, so the reference arm is the oracle PORT (kind "port"); nothing of the CUDA engine runs on that arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_RECS = 10
+WORKLOADS = {  # BASELINE.json configs: users, items, edges, n_layers, aggregator, hidden, out
+    'c1': (10_000, 5_000, 200_000, 2, 'mean', 128, 128),
+    'c2': (1_000_000, 200_000, 50_000_000, 2, 'mean', 128, 128),
+    'c3': (5_000_000, 500_000, 200_000_000, 3, 'pool_nn', 256, 128),
+    'c5': (10_000_000, 1_000_000, 500_000_000, 2, 'mean', 128, 128),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d['hbm_gbs'], tc_burst=d['bf16_tflops'], tc=d['bf16_tflops_sustained'], source='measured')
+    return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [ln.split(', ') for ts, ln in self.lines if t0 <= ts <= t1 + 0.15] or [ln.split(', ') for _, ln in self.lines]
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_reference_sample(n_users, n_items, n_edges, d, budget_s=12.0, max_users=64, seed=0):
+    """Reference-semantics CPU path (oracle port) on a bounded sample, scaled to users/s of the whole job:
+    (a) layer-wise embedding pass on a c1-sized graph, scaled by edge count; (b) the per-user get_recs loop
+    (src/metrics.py:52-77) for a few users against a full-size item table."""
+    from oracle import straightline as O
+    import gnn_recsys_b200 as grb
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    # (a) embeddings on a small graph of the same shape family
+    su, si, se = 10_000, 5_000, 200_000
+    data = grb.make_graph(su, si, se, seed)
+    num = {'user': su, 'item': si}
+    blk = O.block_from_coo(num, num, {c: (s.astype(np.int64), t.astype(np.int64), None) for c, (s, t) in data.relations().items()})
+    g = torch.Generator().manual_seed(seed + 1)
+    sd = {}
+    for t, f in (('user', 2), ('item', 4)):
+        sd['%s_embed.proj_feats.weight' % t] = torch.randn(d, f, generator=g) * 0.5
+        sd['%s_embed.proj_feats.bias' % t] = torch.randn(d, generator=g) * 0.1
+    for et in ('buys', 'bought-by', 'clicks', 'clicked-by'):
+        for nm in ('fc_self', 'fc_neigh'):
+            sd['layers.0.mods.%s.%s.weight' % (et, nm)] = torch.randn(d, d, generator=g) * (2.0 / d) ** 0.5
+    feats = {'user': data.user_feat, 'item': data.item_feat}
+    t0 = time.perf_counter()
+    y = O.get_embeddings_full(num, [blk], feats, sd, d)
+    t_embed_small = time.perf_counter() - t0
+    t_embed_est = t_embed_small * (n_edges / se)
+    # (b) per-user recommendation loop against a full-size item table (cost is data-independent)
+    reps = (n_items + si - 1) // si
+    h_item = y['item'].repeat(reps, 1)[:n_items].contiguous()
+    h_user = y['user']
+    bought = O.create_already_bought(data.relations()[('user', 'buys', 'item')][0], data.relations()[('user', 'buys', 'item')][1])
+    done, t_recs = 0, 0.0
+    while done < max_users and t_recs < budget_s:
+        t0 = time.perf_counter()
+        O.get_recs(h_user, h_item, K_RECS, [done], bought)
+        t_recs += time.perf_counter() - t0
+        done += 1
+    per_user = t_recs / done
+    users_per_s = n_users / (t_embed_est + n_users * per_user)
+    sample = ('oracle port of src/metrics.py:52-77 get_recs loop: %d users x %d items (%.3f s/user) + layer-wise CPU embedding '
+              'pass on a %dx%dx%d graph (%.2f s) scaled by edge count to %.0f s; users/s = U / (t_embed + U * t_user)'
+              % (done, n_items, per_user, su, si, se, t_embed_small, t_embed_est))
+    return dict(value=users_per_s, unit='users/s', cores=cores, kind='port', sample=sample, s_per_user=per_user,
+                embed_s_est=t_embed_est)
+
+
+def run_reference_arm(args, wl_name, wl):
+    n_users, n_items, n_edges, n_layers, agg, hidden, out = wl
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    t_start = time.perf_counter()
+    for step in range(args.warmup + args.steps):
+        base = cpu_reference_sample(n_users, n_items, n_edges, out, budget_s=6.0, max_users=16, seed=step)
+        if step >= args.warmup:
+            vals.append(base['value'])
+    v = float(np.mean(vals))
+    line = {
+        'impl': 'reference', 'metric': 'users/sec for full-graph embed+top-10 recs', 'value': v, 'unit': 'users/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * (time.perf_counter() - t_start) / max(1, args.steps + args.warmup),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(wl_name, wl, args.gpus),
+        'cpu_baseline': dict(base, value=v),
+        'e2e': {'value': v, 'unit': 'users/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, wl, n_gpus):
+    n_users, n_items, n_edges, n_layers, agg, hidden, out = wl
+    return {'workload': '%s: %d users x %d items x %d click/purchase edges, %d-layer ConvModel %s, hidden %d / out %d, '
+                        'full-graph embeddings + top-%d recs for every user' % (name, n_users, n_items, n_edges, n_layers,
+                                                                                 agg, hidden, out, K_RECS),
+            'users': n_users, 'items': n_items, 'edges': n_edges, 'k': K_RECS,
+            'parallelism': 'single GPU' if n_gpus == 1 else 'dst/item id-range sharding x%d, NCCL all-gather + top-k merge' % n_gpus,
+            'l2': 'inputs larger than L2 (CSR + tables >> 126 MB per step), no explicit flush'}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--elem', default='bf16', choices=['bf16', 'fp16'])
+    ap.add_argument('--parts', type=int, default=2, choices=[1, 2])
+    ap.add_argument('--shortlist', type=int, default=16)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-verify', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    wl = WORKLOADS[args.config]
+    if args.impl == 'reference':
+        return run_reference_arm(args, args.config, wl)
+
+    import torch.distributed as dist
+    import gnn_recsys_b200 as grb
+    from gnn_recsys_b200 import distributed as D
+    N = grb._native
+    N.load()  # fails loudly when the CUDA extension is missing
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n_users, n_items, n_edges, n_layers, agg, hidden, out = wl
+    pk = peaks()
+
+    # ---- synthetic data (same on every rank: seeded), device CSR, model
+    t0 = time.perf_counter()
+    data = grb.make_graph_device(n_users, n_items, n_edges, seed=0, device=dev)
+    g = data.graph()
+    for t in g.ntypes:
+        g.nodes[t].data['features'] = g.nodes[t].data['features'].pin_memory()
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    blk = g.full_block_on(dev)
+    torch.cuda.synchronize()
+    t_ingest = time.perf_counter() - t0
+    torch.manual_seed(1)
+    model = grb.ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, agg, 'cos',
+                          'sum', True).to(dev).eval()
+    n_conv = n_layers - 1
+    blocks = [blk] * n_conv
+    buys = data.relations()[('user', 'buys', 'item')]
+    bought = grb.BoughtCSR.from_edges(buys[0], buys[1], n_users)
+    bought.on(dev)
+    cfg = grb.RecsConfig(elem=args.elem, parts=args.parts, shortlist=args.shortlist)
+    feats_dev = {t: g.nodes[t].data['features'].to(dev) for t in g.ntypes}
+    uid_all = np.arange(n_users)
+
+    stage_names = ['embed_in', 'aggregate', 'prep', 'score', 'rescore']
+
+    def resident_step(record=None):
+        """Inputs resident in HBM. Returns (ids, n_overflow); `record` collects CUDA events per stage."""
+        ev = {}
+
+        def mark(name):
+            if record is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev[name] = e
+        mark('t0')
+        h = {t: v for t, v in feats_dev.items()}
+        h = model.embed(h)
+        mark('embed_in')
+        if world == 1:
+            h = model.get_repr(blocks, h)
+        else:
+            h = D.sharded_get_repr(model, blocks, h)
+        mark('aggregate')
+        if world == 1:
+            table = grb.ScoringTable(h['item'], cfg)
+            mark('prep0')
+            ids, scores, n_over = grb.recommend_topk(h['user'], table, K_RECS, bought, return_overflow=True, mark=mark)
+        else:
+            ids, scores, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg)
+            n_over = torch.zeros(1, dtype=torch.int32, device=dev)
+        mark('t1')
+        if record is not None:
+            record.append(ev)
+        return ids, n_over, h
+
+    def e2e_step():
+        """Public API with host features: H2D of the features and D2H of the id table inside the call."""
+        loader = grb.NodeDataLoader(g, {'user': uid_all, 'item': np.arange(n_items)},
+                                    grb.MultiLayerFullNeighborSampler(n_conv), batch_size=None)
+        if world == 1:
+            y = grb.get_embeddings(g, out, model, loader, 1, True, dev, True)
+            ids = grb.get_recs_tensor(g, y, K_RECS, uid_all, bought, True, dev, config=cfg)
+        else:
+            h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
+            h = D.sharded_get_repr(model, blocks, model.embed(h))
+            ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg)
+        return ids.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also the verification pass)
+    for _ in range(max(args.warmup, 1)):
+        ids, n_over, h = resident_step()
+    barrier()
+    verified = None
+    if not args.no_verify and world == 1:
+        sample = torch.from_numpy(np.random.default_rng(0).choice(n_users, 512, replace=False)).to(dev)
+        ex_tab = grb.ScoringTable(h['item'], grb.RecsConfig(exact_only=True))
+        ex_ids, ex_sc = grb.recommend_topk(h['user'][sample], ex_tab, K_RECS, bought.select(sample.cpu().numpy()))
+        hi_n = torch.nn.functional.normalize(h['item'], dim=1)
+        hu_n = torch.nn.functional.normalize(h['user'][sample], dim=1)
+        got = ids[sample].long().clamp(min=0)
+        s_got = (hu_n.unsqueeze(1) * hi_n[got]).sum(-1)
+        s_ex = (hu_n.unsqueeze(1) * hi_n[ex_ids.long().clamp(min=0)]).sum(-1)
+        verified = bool(((s_got - s_ex).abs() < 1e-5).all()) and bool(((ids[sample] < 0) == (ex_ids < 0)).all())
+
+    # ---- timed: resident inputs, CUDA events, max over ranks
+    launches0 = N.kernel_launches()
+    rec = []
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    w0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        ids, n_over, h = resident_step(rec)
+    ev1.record()
+    barrier()
+    w1 = time.perf_counter()
+    launches = N.kernel_launches() - launches0
+    clocks = sampler.stop(w0, w1) if sampler is not None else None
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_users / (ms_step * 1e-3)
+
+    def stage_ms(a, b):
+        return float(np.mean([e[a].elapsed_time(e[b]) for e in rec if a in e and b in e])) if rec and a in rec[0] and b in rec[0] else None
+    stages = {'embed_in_ms': stage_ms('t0', 'embed_in'), 'aggregate_ms': stage_ms('embed_in', 'aggregate')}
+    if world == 1:
+        stages.update({'prep_ms': stage_ms('aggregate', 'score_begin'), 'score_ms': stage_ms('score_begin', 'score_end'),
+                       'rescore_ms': stage_ms('score_end', 't1')})
+
+    # ---- timed: end to end through the public API with host buffers
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids_host = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = sum(int(g.nodes[t].data['features'].numel()) * 4 for t in g.ntypes)
+    d2h = int(ids_host.numel()) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines
+    D_ = hidden
+    e_into = {'item': int(data.is_buy.sum()) + int((~data.is_buy).sum()), 'user': n_edges}
+    agg_bytes = 0
+    for t, n_dst in (('item', n_items), ('user', n_users)):
+        agg_bytes += 2 * 4 * (n_dst + 1) + 4 * n_edges + 4 * D_ * n_edges + 4 * D_ * n_dst + 4 * out * n_dst
+    agg_bytes *= n_conv
+    roof_agg = None
+    if stages.get('aggregate_ms'):
+        gbs = agg_bytes / (stages['aggregate_ms'] * 1e-3) / 1e9 * (1.0 if world == 1 else 1.0)
+        roof_agg = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm'],
+                    'traffic': None, 'algorithmic_bytes': agg_bytes, 'of': pk['source'],
+                    'note': 'all fused CSR gather-reduce + projection kernels of one step (4 relations); bytes = SURVEY 8d B_dst'}
+    flops = 2.0 * n_users * n_items * out
+    roof = None
+    if stages.get('score_ms'):
+        tf = flops / (stages['score_ms'] * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': tf, 'peak': pk['tc'], 'unit': 'TFLOP/s', 'frac': tf / pk['tc'],
+                'traffic': None, 'executed_tflops': tf * (3 if args.parts == 2 else 1),
+                'executed_frac': tf * (3 if args.parts == 2 else 1) / pk['tc'], 'of': pk['source'] + ' (sustained)',
+                'kernel': 'score_topk_kernel (tcgen05 %s, %d-product, fused top-%d shortlist)' % (args.elem, 3 if args.parts == 2 else 1, args.shortlist),
+                'note': 'achieved counts 2*U*I*D once; the %d-product split executes %dx that on the tensor pipe' % (3 if args.parts == 2 else 1, 3 if args.parts == 2 else 1)}
+    elif roof_agg is not None:
+        roof = roof_agg
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_reference_sample(n_users, n_items, n_edges, out)
+
+    line = {
+        'metric': 'users/sec for full-graph embed+top-10 recs', 'value': value, 'unit': 'users/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 embeddings + %s%s scoring (f32 accumulate, f32 re-score)' % (args.elem, 'x3' if args.parts == 2 else ''),
+        'data': 'synthetic', 'config': workload_config(args.config, wl, world),
+        'e2e': {'value': n_users / e2e_s, 'unit': 'users/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_s * 1e3},
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_aggregation': roof_agg,
+        'cpu_baseline': cpu, 'stages_ms': stages, 'overflow_users': int(n_over.item()), 'verified_vs_exact_fp32': verified,
+        'setup_s': {'generate': t_gen, 'ingest_csr_build': t_ingest},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

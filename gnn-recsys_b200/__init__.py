@@ -3,7 +3,7 @@
 Import as ``gnn_recsys_b200`` (the repo-root alias module) -- the directory name carries a hyphen.
 """
 from .graph import HeteroGraph, Block, Relation, heterograph, edge_graph, csr_by_dst_host, NID, EID  # noqa: F401
-from .synthetic import make_graph, SyntheticData, CONFIGS  # noqa: F401
+from .synthetic import make_graph, make_graph_device, SyntheticData, CONFIGS  # noqa: F401
 from .dataloading import (MultiLayerFullNeighborSampler, MultiLayerNeighborSampler, NodeDataLoader,  # noqa: F401
                           EdgeDataLoader, negative_sampler, to_block)
 from .model import (ConvModel, ConvLayer, NodeEmbedding, HeteroGraphConv, CosinePrediction,  # noqa: F401
@@ -11,4 +11,4 @@ from .model import (ConvModel, ConvLayer, NodeEmbedding, HeteroGraphConv, Cosine
 from .train.run import get_embeddings  # noqa: F401
 from .metrics import get_recs, get_recs_tensor, create_already_bought, create_already_bought_csr  # noqa: F401
 from .recs import RecsConfig, BoughtCSR, ScoringTable, recommend_topk  # noqa: F401
-from . import ops, _native  # noqa: F401
+from . import ops, _native, distributed  # noqa: F401

@@ -27,6 +27,7 @@ _i32, _i64, _f32, _sz, _vp = C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_vo
 SIGNATURES = {
     'gr_last_error': (C.c_char_p, []),
     'gr_version': (C.c_int, []),
+    'gr_launch_count': (C.c_longlong, []),
     'gr_device_info': (C.c_int, [_vp, _vp, _vp]),
     'gr_linear_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, C.c_int, _vp, _vp]),
     'gr_sage_relation_workspace_bytes': (_sz, [_i64, _i32]),
@@ -110,6 +111,11 @@ def call(name: str, *args):
 def workspace(nbytes: int, device) -> torch.Tensor:
     """256-byte aligned scratch buffer owned by the caller (torch's caching allocator aligns to 512 B)."""
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def kernel_launches() -> int:
+    """Kernels launched by the library in this process."""
+    return int(load().gr_launch_count())
 
 
 def device_info():

@@ -11,6 +11,7 @@
 namespace gr {
 
 void set_error(const std::string& msg);
+void count_launch();  // every kernel launch of the library bumps gr_launch_count()
 
 #define GR_REQUIRE(cond, code, msg)                                                   \
   do {                                                                                \
@@ -31,6 +32,7 @@ void set_error(const std::string& msg);
 
 #define GR_LAUNCH_CHECK()                                                             \
   do {                                                                                \
+    ::gr::count_launch();                                                             \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess) {                                                         \
       ::gr::set_error(std::string(__func__) + ": kernel launch: " + cudaGetErrorString(e__)); \

@@ -1,0 +1,104 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, ``torch.distributed`` (NCCL over NVLink) plumbing.
+
+The reference is single-process; this module introduces the one strategy the path needs:
+
+  * embedding layers -- every destination row is independent given the previous layer's rows, so each node type's
+    destination id space is cut into ``world`` equal contiguous ranges; rank p runs the fused relation kernels on
+    its range only (``row_begin`` / ``row_end`` of ``gr_sage_relation_f32``) and the layer output is all-gathered
+    (one in-place ``all_gather_into_tensor`` per node type per layer, tables padded to ``world * chunk`` rows).
+  * scoring -- the item table is sharded by the same contiguous ranges; each rank scores ALL users against its
+    item shard (tcgen05 GEMM + shortlist + exact re-score = exact per-shard top-k), the per-shard lists travel to
+    the rank that owns the user range (one ``all_to_all_single`` for ids, one for scores) and are merged there by
+    ``gr_topk_merge`` ((score desc, id asc) -- the same total order as a single-GPU run).
+
+No collective sits inside a kernel yet: the exchanged volumes are tiny next to the compute
+(c2: 0.6 GB of embeddings, 80 MB of top-k lists per step).
+
+The exchange helpers are backend-agnostic (``gloo`` on CPU in tests/test_distributed.py, ``nccl`` on GPUs).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def chunk_rows(n: int, world: int) -> int:
+    return (n + world - 1) // world
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous id range ``[begin, end)`` owned by ``rank`` (equal chunks, the last ones may be short/empty)."""
+    c = chunk_rows(n, world)
+    return min(rank * c, n), min((rank + 1) * c, n)
+
+
+def allgather_rows(local_full: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """``local_full``: ``[n, d]`` table in which only this rank's ``shard_range`` rows are valid. Returns the
+    ``[n, d]`` table with every rank's rows filled in (view of a padded ``[world * chunk, d]`` buffer)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return local_full
+    c = chunk_rows(n, world)
+    b, e = shard_range(n, world, rank)
+    full = local_full.new_empty((world * c, local_full.shape[1]))
+    mine = full[rank * c:(rank + 1) * c]
+    mine[:e - b].copy_(local_full[b:e])
+    if e - b < c:
+        mine[e - b:].zero_()
+    if dist.get_backend(group) == 'gloo':  # gloo has no all_gather_into_tensor
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous(), group=group)
+        full = torch.cat(parts, 0)
+    else:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n]
+
+
+def exchange_topk(ids: torch.Tensor, scores: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor, int, int]:
+    """``ids`` / ``scores``: ``[n_users, k]`` per-shard top-k of ALL users on this rank. Sends each user range to its
+    owner; returns ``(ids [world, chunk, k], scores [world, chunk, k], begin, end)`` for this rank's user range
+    (rows past ``end - begin`` are padding: id -1, score -inf)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n, k = ids.shape
+    c = chunk_rows(n, world)
+    b, e = shard_range(n, world, rank)
+    if world == 1:
+        return ids.unsqueeze(0), scores.unsqueeze(0), b, e
+    pad = world * c - n
+    if pad:
+        ids = torch.cat([ids, ids.new_full((pad, k), -1)], 0)
+        scores = torch.cat([scores, scores.new_full((pad, k), float('-inf'))], 0)
+    out_ids, out_scores = torch.empty_like(ids), torch.empty_like(scores)
+    dist.all_to_all_single(out_ids, ids.contiguous(), group=group)
+    dist.all_to_all_single(out_scores, scores.contiguous(), group=group)
+    return out_ids.view(world, c, k), out_scores.view(world, c, k), b, e
+
+
+def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """``ConvModel.get_repr`` with destination-range sharding: returns full (all-gathered) tables on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    for i, blk in enumerate(blocks):
+        ranges = {t: shard_range(blk.number_of_dst_nodes(t), world, rank) for t in blk.dsttypes}
+        out = model.layers[i](blk, h, ranges)
+        h = {t: allgather_rows(v, v.shape[0], group) for t, v in out.items()}
+    return h
+
+
+def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought=None, config=None, group=None):
+    """Item-range-sharded scoring + owner-side merge. ``h_user`` / ``h_item`` are the full tables (every rank holds
+    them after the last all-gather); ``bought`` rows follow ``h_user`` rows. Returns ``(ids [u_loc, k], scores,
+    (begin, end))`` for the user range this rank owns."""
+    from . import ops
+    from .recs import RecsConfig, ScoringTable, recommend_topk
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cfg = config or RecsConfig()
+    ib, ie = shard_range(h_item.shape[0], world, rank)
+    table = ScoringTable(h_item[ib:ie], cfg, item_id_base=ib)
+    ids, scores = recommend_topk(h_user, table, k, bought)
+    all_ids, all_scores, ub, ue = exchange_topk(ids, scores, group)
+    if world == 1:
+        return ids, scores, (ub, ue)
+    m_scores, m_ids = ops.topk_merge(all_scores.contiguous(), all_ids.contiguous(), k)
+    return m_ids[:ue - ub], m_scores[:ue - ub], (ub, ue)

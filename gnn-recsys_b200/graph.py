@@ -357,10 +357,23 @@ class HeteroGraph:
     def full_block_on(self, device, edge_weight: Optional[str] = None) -> Block:
         """Device-resident full-graph block, built once per (device, edge weight) and kept: the graph structure
         stays in HBM across ``get_embeddings`` calls instead of being re-sent per batch (``run.py:338-339``).
+        The COO lists go to the device as int32 and the stable CSR is built there (``gr_csr_build_i32``).
         Node features are NOT cached here -- they travel with each call."""
         key = (str(device), edge_weight)
         if key not in self._dev_blocks:
-            self._dev_blocks[key] = self.full_block(edge_weight, with_features=False).to(device)
+            from . import ops
+            rels = {}
+            for c, (s, d) in self._edges.items():
+                if s.shape[0] > INT32_MAX or max(self._num[c[0]], self._num[c[2]]) > INT32_MAX:
+                    raise OverflowError('int32 CSR cannot index relation %r' % (c,))
+                src = torch.from_numpy(s.astype(np.int32, copy=False)).to(device)
+                dst = torch.from_numpy(d.astype(np.int32, copy=False)).to(device)
+                indptr, indices, eperm = ops.csr_build(src, dst, self._num[c[2]])
+                w = None
+                if edge_weight is not None and edge_weight in self._edge_frames[c]:
+                    w = self._edge_frames[c][edge_weight].to(device).to(torch.float32).reshape(-1)[eperm.long()].contiguous()
+                rels[c] = Relation(indptr, indices, self._num[c[0]], self._num[c[2]], eperm, w)
+            self._dev_blocks[key] = Block(rels, self._num, self._num)
         return self._dev_blocks[key]
 
     def device_edges(self, etype, device):

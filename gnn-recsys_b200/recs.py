@@ -132,10 +132,12 @@ class ScoringTable:
 
 
 def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Optional[BoughtCSR] = None,
-                   return_overflow: bool = False):
+                   return_overflow: bool = False, mark=None):
     """Top-``k`` items of ``table`` for every row of ``h_user`` (``[n, d]`` fp32, CUDA): ``(ids int32 [n, k],
     scores fp32 [n, k])`` sorted by (score desc, id asc); ``-1`` / ``-inf`` pad rows with fewer than k candidates.
-    ``bought`` rows must follow ``h_user`` rows. ids are global (``table.item_id_base`` added)."""
+    ``bought`` rows must follow ``h_user`` rows. ids are global (``table.item_id_base`` added).
+    ``mark(name)`` (optional) is called between stages -- bench.py records CUDA events with it."""
+    mark = mark or (lambda name: None)
     cfg = table.cfg
     h_user = h_user.contiguous()
     n = h_user.shape[0]
@@ -150,8 +152,10 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
     if shortlist > 32:
         raise ValueError('k / shortlist above 32 is not supported by the fused top-k epilogue')
     users_q, _ = ops.score_prep(h_user, None, table.d_pad, cfg.parts, cfg.elem_type, False)
+    mark('score_begin')
     sl_score, sl_id = ops.score_topk_tc(users_q, table.items_q, table.item_id_base, table.d_pad, cfg.parts,
                                         cfg.elem_type, bptr, bids, shortlist)
+    mark('score_end')
     ids, scores, overflow, n_overflow = ops.rescore_topk(
         h_user, table.h_item, table.item_id_base, table.center, sl_score, sl_id, table.stats, cfg.err_rel(),
         cfg.err_abs(table.d), cfg.tie_tol, k, COS_EPS)

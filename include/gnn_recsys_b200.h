@@ -39,6 +39,8 @@ enum { GR_ACC_STORE = 0, GR_ACC_ADD = 1, GR_ACC_MAX = 2 }; /* HeteroGraphConv ag
 
 const char* gr_last_error(void);
 int gr_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+long long gr_launch_count(void);
 /* sm count / compute capability of the current device; GR_E_UNSUPPORTED unless it is sm_100. */
 int gr_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 
