@@ -24,6 +24,7 @@
 //   * small user counts: the item range is split over blockIdx.y so the grid still fills the chip; the per-split
 //     shortlists are merged by gr_topk_merge (host side of this file).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -89,7 +90,7 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -124,82 +125,90 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format) {
          ((uint32_t)(TILE_M >> 4) << 24);
 }
 
-// ---- per-row state of the slow path; column t = row within the CTA ------------------------------------------
-struct RowState {
-  long long* bp;    // [256] cursor into bought_ids
-  long long* bend;  // [256] end of the row's bought range
-  int* nb;          // [256] bought id at the cursor (INT_MAX when exhausted)
-  const int* bought_ids;
-  int S;
-};
+// v[i] for a run-time i over a register array: binary select tree (N - 1 selects), no local memory
+template <int N>
+__device__ __forceinline__ uint32_t select_n(const uint32_t* v, int i) {
+  if constexpr (N == 1) {
+    return v[0];
+  } else {
+    const uint32_t lo = select_n<N / 2>(v, i), hi = select_n<N / 2>(v + N / 2, i);
+    return (i & (N / 2)) ? hi : lo;
+  }
+}
+__device__ __forceinline__ uint32_t select32(const uint32_t* v, int i) { return select_n<32>(v, i); }
 
-// Slow path (rare): candidate `s` beat the row threshold. ls / li = the row's shortlist (S scores descending, S ids).
-// Returns the new threshold (S-th best so far).
-__device__ __noinline__ float shortlist_insert(float s, int gid, int t, const RowState* rs, float* __restrict__ ls,
-                                               int* __restrict__ li) {
-  const int S = rs->S;
-  if (gid >= rs->nb[t]) {  // may be an already-bought item: advance the cursor to the first id >= gid
-    long long lo = rs->bp[t], hi = rs->bend[t];
-    const long long end = hi;
+// ---- slow path -------------------------------------------------------------------------------------------------
+// Candidate `s` (item `gid`) beat the threshold of CTA row `t`. The row's shortlist is column t of ls / li
+// ([S][256] in shared memory, scores descending). s_nb[t] caches the smallest already-bought id >= the last id
+// looked up, so the common case of the bought test is one compare. Returns the new threshold (S-th best so far).
+__device__ __noinline__ float shortlist_insert(float s, int gid, int t, int S, float* __restrict__ ls,
+                                               int* __restrict__ li, int* __restrict__ s_nb, long long b0,
+                                               long long b1, const int* __restrict__ bought_ids) {
+  if (gid >= s_nb[t]) {  // may be an already-bought item: first bought id >= gid
+    long long lo = b0, hi = b1;
     while (lo < hi) {
       const long long mid = (lo + hi) >> 1;
-      if (rs->bought_ids[mid] < gid) lo = mid + 1; else hi = mid;
+      if (bought_ids[mid] < gid) lo = mid + 1; else hi = mid;
     }
-    const bool is_bought = lo < end && rs->bought_ids[lo] == gid;
+    const bool is_bought = lo < b1 && bought_ids[lo] == gid;
     long long nxt = lo;
     if (is_bought)  // skip duplicates of the same id (multi-edges)
-      while (nxt < end && rs->bought_ids[nxt] == gid) ++nxt;
-    rs->bp[t] = nxt;
-    rs->nb[t] = nxt < end ? rs->bought_ids[nxt] : 0x7fffffff;
-    if (is_bought) return ls[S - 1];
+      while (nxt < b1 && bought_ids[nxt] == gid) ++nxt;
+    s_nb[t] = nxt < b1 ? bought_ids[nxt] : 0x7fffffff;
+    if (is_bought) return ls[(S - 1) * ROWS_PER_CTA + t];
   }
-  int j = S - 1;
-  while (j > 0 && ls[j - 1] < s) {
-    ls[j] = ls[j - 1];
-    li[j] = li[j - 1];
-    --j;
+  int lo = 0, hi = S - 1;  // first position whose score is < s (equal scores keep the earlier, smaller id first)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ls[mid * ROWS_PER_CTA + t] >= s) lo = mid + 1; else hi = mid;
   }
-  ls[j] = s;
-  li[j] = gid;
-  return ls[S - 1];
+  for (int j = S - 1; j > lo; --j) {
+    ls[j * ROWS_PER_CTA + t] = ls[(j - 1) * ROWS_PER_CTA + t];
+    li[j * ROWS_PER_CTA + t] = li[(j - 1) * ROWS_PER_CTA + t];
+  }
+  ls[lo * ROWS_PER_CTA + t] = s;
+  li[lo * ROWS_PER_CTA + t] = gid;
+  return ls[(S - 1) * ROWS_PER_CTA + t];
 }
 
+// Shared-memory plan: [A: UT x PARTS x KB sub-tiles][B ring: `ring` sub-tiles of 16 KB][shortlists][next-bought][barriers]
+constexpr int MAX_RING = 8;
 template <int KB, int PARTS>
 struct Cfg {
   static constexpr int A_BYTES = UT * PARTS * KB * SUB_BYTES;
-  static constexpr int CHUNK_BYTES = KB * SUB_BYTES;  // one part of one B tile
-  static constexpr int TAIL_BYTES = ROWS_PER_CTA * 20 + 512;
-  static constexpr int RING_RAW = (SMEM_LIMIT - 1024 - A_BYTES - TAIL_BYTES) / CHUNK_BYTES;
-  static constexpr int RING = RING_RAW > 6 ? 6 : RING_RAW;
-  static constexpr int B_BYTES = RING * CHUNK_BYTES;
-  static constexpr size_t SMEM = 1024 /*alignment slack*/ + A_BYTES + B_BYTES + TAIL_BYTES;
-  static_assert(RING >= 2, "B ring needs at least two chunks");
+  static constexpr int TAIL_BYTES = ROWS_PER_CTA * 4 + 512;  // s_nb + barriers
+  static int list_bytes(int S) { return S * ROWS_PER_CTA * 8; }
+  static int ring(int S) {
+    const int r = (SMEM_LIMIT - 1024 - A_BYTES - list_bytes(S) - TAIL_BYTES) / SUB_BYTES;
+    return r > MAX_RING ? MAX_RING : r;
+  }
+  static size_t smem(int S) { return 1024 /*alignment slack*/ + A_BYTES + (size_t)ring(S) * SUB_BYTES + list_bytes(S) + TAIL_BYTES; }
 };
 
-template <int KB, int PARTS>
+// MODE (debug / profiling only, see DESIGN.md "pipeline experiments"): 0 = product kernel; 1 = epilogue reads TMEM but
+// skips the top-k scan; 2 = epilogue releases the accumulator without reading it; 3 = MMA warp commits without MMAs.
+template <int KB, int PARTS, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_constant__ CUtensorMap tm_items,
                   long long n_users, long long n_items, long long item_id_base, int tiles_per_split, uint32_t idesc,
-                  const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S,
+                  const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int ring,
                   float* __restrict__ sl_score, int* __restrict__ sl_id) {
   using L = Cfg<KB, PARTS>;
-  constexpr int RING = L::RING;
   constexpr int D_PAD = KB * KBLK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
   uint8_t* sB = sA + L::A_BYTES;
-  long long* s_bp = reinterpret_cast<long long*>(sB + L::B_BYTES);
-  long long* s_bend = s_bp + ROWS_PER_CTA;
-  int* s_nb = reinterpret_cast<int*>(s_bend + ROWS_PER_CTA);
+  float* ls = reinterpret_cast<float*>(sB + ring * SUB_BYTES);  // [S][256]
+  int* li = reinterpret_cast<int*>(ls + S * ROWS_PER_CTA);       // [S][256]
+  int* s_nb = li + S * ROWS_PER_CTA;                              // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_nb + ROWS_PER_CTA);
-  uint64_t* full = bars;                // [RING]    TMA -> MMA
-  uint64_t* empty = full + RING;        // [RING]    MMA -> TMA
-  uint64_t* a_full = empty + RING;      // [1]
-  uint64_t* t_full = a_full + 1;        // [UT][2]   MMA -> epilogue
-  uint64_t* t_empty = t_full + UT * 2;  // [UT][2]   epilogue -> MMA
+  uint64_t* full = bars;                  // [MAX_RING]  TMA -> MMA
+  uint64_t* empty = full + MAX_RING;      // [MAX_RING]  MMA -> TMA
+  uint64_t* a_full = empty + MAX_RING;    // [1]
+  uint64_t* t_full = a_full + 1;          // [UT][2]     MMA -> epilogue
+  uint64_t* t_empty = t_full + UT * 2;    // [UT][2]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + UT * 2);
-  __shared__ RowState rs;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_all = (int)((n_items + TILE_N - 1) / TILE_N);
@@ -208,11 +217,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   const long long row_base = (long long)blockIdx.x * ROWS_PER_CTA;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RING; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < ring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(a_full, 1);
     for (int i = 0; i < UT * 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    rs.bp = s_bp; rs.bend = s_bend; rs.nb = s_nb; rs.bought_ids = bought_ids; rs.S = S;
   }
   if (warp == 1) {  // TMEM allocation: all 512 columns (this kernel runs one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
@@ -224,7 +232,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer: one 16 KB sub-tile (64 K-elements of one part of one item tile) per ring slot
     if (lane == 0 && n_tiles > 0) {
       mbar_expect_tx(a_full, L::A_BYTES);
       for (int ut = 0; ut < UT; ++ut)
@@ -232,16 +240,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
           for (int kb = 0; kb < KB; ++kb)
             tma_load_2d(sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES, &tm_users, pa * D_PAD + kb * KBLK,
                         (int)(row_base + ut * TILE_M), a_full);
-      int g = 0;
+      int buf = 0;
+      uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
-        for (int pb = 0; pb < PARTS; ++pb, ++g) {
-          const int buf = g % RING;
-          const uint32_t phase = (uint32_t)(g / RING) & 1u;
-          mbar_wait(empty + buf, phase ^ 1u);
-          mbar_expect_tx(full + buf, L::CHUNK_BYTES);
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_2d(sB + buf * L::CHUNK_BYTES + kb * SUB_BYTES, &tm_items, pb * D_PAD + kb * KBLK,
-                        (tile0 + j) * TILE_N, full + buf);
+        for (int pb = 0; pb < PARTS; ++pb) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(empty + buf, phase ^ 1u);
+            mbar_expect_tx(full + buf, SUB_BYTES);
+            tma_load_2d(sB + buf * SUB_BYTES, &tm_items, pb * D_PAD + kb * KBLK, (tile0 + j) * TILE_N, full + buf);
+            if (++buf == ring) { buf = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -250,37 +258,38 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
     if (lane == 0 && n_tiles > 0) {
       mbar_wait(a_full, 0);
       tc_fence_after();
-      int g = 0;
+      int buf = 0;
+      uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         const int slot = j & 1;
         const uint32_t aphase = (uint32_t)(j >> 1) & 1u;
-        for (int pb = 0; pb < PARTS; ++pb, ++g) {
-          const int buf = g % RING;
-          const uint32_t phase = (uint32_t)(g / RING) & 1u;
-          mbar_wait(full + buf, phase);
-          tc_fence_after();
-          for (int ut = 0; ut < UT; ++ut) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)((ut * 2 + slot) * TILE_N);
-            if (pb == 0) {  // accumulator slot must have been drained by the epilogue of tile j - 2
-              mbar_wait(t_empty + ut * 2 + slot, aphase ^ 1u);
-              tc_fence_after();
-            }
-            // B part 0 (hi) pairs with every A part; B part 1 (lo) pairs with A hi only: hi.hi + lo.hi + hi.lo
-            const int n_pa = pb == 0 ? PARTS : 1;
-            for (int pa = 0; pa < n_pa; ++pa) {
+        for (int pb = 0; pb < PARTS; ++pb) {
 #pragma unroll
-              for (int kb = 0; kb < KB; ++kb) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(full + buf, phase);
+            tc_fence_after();
+            const uint64_t db = make_desc_sw128(smem_u32(sB + buf * SUB_BYTES));
+            for (int ut = 0; ut < UT; ++ut) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((ut * 2 + slot) * TILE_N);
+              if (pb == 0 && kb == 0) {  // accumulator slot must have been drained by the epilogue of tile j - 2
+                mbar_wait(t_empty + ut * 2 + slot, aphase ^ 1u);
+                tc_fence_after();
+              }
+              // B part 0 (hi) pairs with every A part; B part 1 (lo) pairs with A hi only: hi.hi + lo.hi + hi.lo
+              const int n_pa = pb == 0 ? PARTS : 1;
+              for (int pa = 0; pa < n_pa; ++pa) {
                 const uint64_t da = make_desc_sw128(smem_u32(sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES));
-                const uint64_t db = make_desc_sw128(smem_u32(sB + buf * L::CHUNK_BYTES + kb * SUB_BYTES));
 #pragma unroll
                 for (int k = 0; k < KBLK / UMMA_K; ++k)  // +32 bytes (>>4 = 2) per K = 16 step inside the swizzle atom
-                  tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                             (pb | pa | kb | k) != 0 ? 1u : 0u);
+                  if (MODE != 3)
+                    tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                               (pb | kb | pa | k) != 0 ? 1u : 0u);
               }
+              if (pb == PARTS - 1 && kb == KB - 1) tc_commit(t_full + ut * 2 + slot);
             }
-            if (pb == PARTS - 1) tc_commit(t_full + ut * 2 + slot);
+            tc_commit(empty + buf);
+            if (++buf == ring) { buf = 0; phase ^= 1u; }
           }
-          tc_commit(empty + buf);
         }
       }
     }
@@ -292,60 +301,76 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
     const int t = ut * TILE_M + q * 32 + lane;
     const long long row = row_base + t;
     const bool live = row < n_users;
-    // the row's shortlist lives in the output arrays: [split][row][S]
-    float* ls = sl_score + ((long long)blockIdx.y * n_users + (live ? row : 0)) * S;
-    int* li = sl_id + ((long long)blockIdx.y * n_users + (live ? row : 0)) * S;
-    if (live)
-      for (int s = 0; s < S; ++s) { ls[s] = -INFINITY; li[s] = -1; }
+    for (int s = 0; s < S; ++s) { ls[s * ROWS_PER_CTA + t] = -INFINITY; li[s * ROWS_PER_CTA + t] = -1; }
+    long long b0 = 0, b1 = 0;
+    if (live && bought_indptr != nullptr) { b0 = bought_indptr[row]; b1 = bought_indptr[row + 1]; }
     {
-      long long lo = 0, end = 0;
-      if (live && bought_indptr != nullptr) {
-        lo = bought_indptr[row]; end = bought_indptr[row + 1];
-        long long hi = end;  // first bought id >= first item id of this CTA's range
-        const long long first_id = item_id_base + (long long)tile0 * TILE_N;
-        while (lo < hi) {
-          const long long mid = (lo + hi) >> 1;
-          if ((long long)bought_ids[mid] < first_id) lo = mid + 1; else hi = mid;
-        }
+      long long lo = b0, hi = b1;  // first bought id >= first item id of this CTA's range
+      const long long first_id = item_id_base + (long long)tile0 * TILE_N;
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((long long)bought_ids[mid] < first_id) lo = mid + 1; else hi = mid;
       }
-      s_bp[t] = lo; s_bend[t] = end;
-      s_nb[t] = lo < end ? bought_ids[lo] : 0x7fffffff;
+      s_nb[t] = lo < b1 ? bought_ids[lo] : 0x7fffffff;
     }
     float tau = live ? -INFINITY : INFINITY;
-    const long long id_end = item_id_base + n_items;
+    const int id_end = (int)(item_id_base + n_items);
     __syncwarp();
     for (int j = 0; j < n_tiles; ++j) {
       const int slot = j & 1;
       const uint32_t aphase = (uint32_t)(j >> 1) & 1u;
+      const bool partial = (long long)(tile0 + j + 1) * TILE_N > n_items;  // last tile: columns past n_items are zero fill
       mbar_wait(t_full + ut * 2 + slot, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ut * 2 + slot) * TILE_N);
-#pragma unroll 1
-      for (int c = 0; c < TILE_N / 32; ++c) {
-        uint32_t v[32];
-        tc_ld32(taddr + (uint32_t)(c * 32), v);
+      // drain the whole accumulator row into registers, then hand the TMEM slot straight back to the MMA warp:
+      // the scan below (and its data-dependent slow path) never holds up the tensor pipe
+      uint32_t v[TILE_N];
+      if (MODE != 2) {
+#pragma unroll
+        for (int c = 0; c < TILE_N / 32; ++c) tc_ld32(taddr + (uint32_t)(c * 32), v + c * 32);
         tc_ld_wait();
-        if (c == TILE_N / 32 - 1) {  // accumulator fully read: hand the TMEM slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + ut * 2 + slot);
-        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + ut * 2 + slot);
+      if (MODE == 2) continue;
+      if (MODE == 1) {
+        if (__uint_as_float(v[lane]) == 123456.f) tau = 0.f;  // keep the loads alive
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < TILE_N / 32; ++c) {
         float m[11];
 #pragma unroll
         for (int i = 0; i < 10; ++i)
-          m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-        m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+          m[i] = max3(__uint_as_float(v[c * 32 + 3 * i]), __uint_as_float(v[c * 32 + 3 * i + 1]),
+                      __uint_as_float(v[c * 32 + 3 * i + 2]));
+        m[10] = fmaxf(__uint_as_float(v[c * 32 + 30]), __uint_as_float(v[c * 32 + 31]));
         const float mx = max3(max3(m[0], m[1], m[2]), max3(m[3], m[4], m[5]),
                               max3(max3(m[6], m[7], m[8]), m[9], m[10]));
         if (mx > tau) {
-          const long long id0 = item_id_base + (long long)(tile0 + j) * TILE_N + c * 32;
+          // Rare after the first tiles, and deliberately COMPACT code (a bit mask + a select tree instead of one call
+          // site per column): the slow path runs cold, so its cost is instruction-cache lines, not instructions.
+          const int id0 = (int)(item_id_base + (long long)(tile0 + j) * TILE_N) + c * 32;
+          uint32_t cand = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(v[i]);
-            if (s > tau && id0 + i < id_end) tau = shortlist_insert(s, (int)(id0 + i), t, &rs, ls, li);
+          for (int i = 0; i < 32; ++i)
+            if (__uint_as_float(v[c * 32 + i]) > tau) cand |= 1u << i;
+          if (partial) cand &= (id_end - id0 >= 32) ? 0xffffffffu : (id_end > id0 ? (1u << (id_end - id0)) - 1u : 0u);
+          while (cand != 0) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float s = __uint_as_float(select32(v + c * 32, i));
+            if (s > tau) tau = shortlist_insert(s, id0 + i, t, S, ls, li, s_nb, b0, b1, bought_ids);
           }
         }
       }
+    }
+    if (live) {  // [split][row][S]
+      float* os = sl_score + ((long long)blockIdx.y * n_users + row) * S;
+      int* oi = sl_id + ((long long)blockIdx.y * n_users + row) * S;
+      for (int s = 0; s < S; ++s) { os[s] = ls[s * ROWS_PER_CTA + t]; oi[s] = li[s * ROWS_PER_CTA + t]; }
     }
   }
   tc_fence_before();
@@ -402,15 +427,17 @@ struct ScoreArgs {
   int* sl_id;
 };
 
-template <int KB, int PARTS>
+template <int KB, int PARTS, int MODE = 0>
 int launch_score(const ScoreArgs& a, cudaStream_t st) {
-  auto kern = score_topk_kernel<KB, PARTS>;
-  const size_t smem = Cfg<KB, PARTS>::SMEM;
-  static_assert(Cfg<KB, PARTS>::SMEM <= SMEM_LIMIT, "shared memory budget exceeded");
+  auto kern = score_topk_kernel<KB, PARTS, MODE>;
+  using L = Cfg<KB, PARTS>;
+  const int ring = L::ring(a.S);
+  GR_REQUIRE(ring >= 2, GR_E_INVALID, "shortlist too large for the shared-memory budget of this configuration");
+  const size_t smem = L::smem(a.S);
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((a.n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA), (unsigned)a.splits);
   kern<<<grid, NUM_THREADS, smem, st>>>(a.mu, a.mi, a.n_users, a.n_items, a.item_id_base, a.tiles_per_split, a.idesc,
-                                        a.bptr, a.bids, a.S, a.sl_score, a.sl_id);
+                                        a.bptr, a.bids, a.S, ring, a.sl_score, a.sl_id);
   GR_LAUNCH_CHECK();
   return GR_OK;
 }
@@ -488,7 +515,12 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
     part_id = reinterpret_cast<int*>(static_cast<char*>(ws) + half);
   }
   a.sl_score = part_score; a.sl_id = part_id;
-  if (d_pad == 64) rc = parts == 1 ? launch_score<1, 1>(a, st) : launch_score<1, 2>(a, st);
+  static const int debug_mode = getenv("GR_SCORE_DEBUG_MODE") ? atoi(getenv("GR_SCORE_DEBUG_MODE")) : 0;
+  if (debug_mode != 0 && d_pad == 128 && parts == 2) {  // pipeline experiments (results are NOT valid top-k lists)
+    rc = debug_mode == 1 ? launch_score<2, 2, 1>(a, st) : debug_mode == 2 ? launch_score<2, 2, 2>(a, st) : launch_score<2, 2, 3>(a, st);
+  } else if (debug_mode != 0 && d_pad == 128 && parts == 1) {
+    rc = debug_mode == 1 ? launch_score<2, 1, 1>(a, st) : debug_mode == 2 ? launch_score<2, 1, 2>(a, st) : launch_score<2, 1, 3>(a, st);
+  } else if (d_pad == 64) rc = parts == 1 ? launch_score<1, 1>(a, st) : launch_score<1, 2>(a, st);
   else rc = parts == 1 ? launch_score<2, 1>(a, st) : launch_score<2, 2>(a, st);
   if (rc != GR_OK) return rc;
   if (a.splits > 1)
