@@ -132,6 +132,15 @@ int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_list_or_nul
 int gr_topk_merge(const float* scores, const int32_t* ids, int32_t parts, int64_t n_users, int32_t k_in,
                   int32_t k_out, float* out_scores, int32_t* out_ids, gr_stream_t stream);
 
+/* ---- graph ingest next to the path: stable COO -> int32 CSR over destination rows on the
+ *      device, replacing what dgl.heterograph (src/builder.py:377-383) + DGL's lazy CSC build behind update_all do on
+ *      the CPU. LSD radix sort of (dst, edge id): neighbours of a row stay in edge-id order (bit-exact against a
+ *      stable argsort). eperm[j] = edge id stored in CSR slot j; indices[j] = src[eperm[j]]; indptr has n_dst + 1
+ *      entries. src / dst are int32 device arrays with 0 <= dst < n_dst. */
+size_t gr_csr_build_workspace_bytes(int64_t nnz, int32_t n_dst);
+int gr_csr_build_i32(const int32_t* src, const int32_t* dst, int64_t nnz, int32_t n_dst, int32_t* indptr,
+                     int32_t* indices, int32_t* eperm, void* ws, size_t ws_bytes, gr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
