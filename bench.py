@@ -41,6 +41,10 @@ WORKLOADS = {  # BASELINE.json configs: users, items, edges, n_layers, aggregato
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+DRAM_TRAFFIC = {}
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -258,17 +262,20 @@ def main():
             mark('prep0')
             ids, scores, n_over = grb.recommend_topk(h['user'], table, K_RECS, bought, return_overflow=True, mark=mark)
         else:
-            ids, scores, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg)
+            mark('prep0')
+            ids, scores, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark)
             n_over = torch.zeros(1, dtype=torch.int32, device=dev)
         mark('t1')
         if record is not None:
             record.append(ev)
         return ids, n_over, h
 
+    loader = grb.NodeDataLoader(g, {'user': uid_all, 'item': np.arange(n_items)},
+                                grb.MultiLayerFullNeighborSampler(n_conv), batch_size=None)
+    ids_pinned = torch.empty((D.chunk_rows(n_users, world), K_RECS), dtype=torch.int32).pin_memory()
+
     def e2e_step():
-        """Public API with host features: H2D of the features and D2H of the id table inside the call."""
-        loader = grb.NodeDataLoader(g, {'user': uid_all, 'item': np.arange(n_items)},
-                                    grb.MultiLayerFullNeighborSampler(n_conv), batch_size=None)
+        """Public API with host features (pinned): H2D of the features and D2H of the id table inside the call."""
         if world == 1:
             y = grb.get_embeddings(g, out, model, loader, 1, True, dev, True)
             ids = grb.get_recs_tensor(g, y, K_RECS, uid_all, bought, True, dev, config=cfg)
@@ -276,7 +283,10 @@ def main():
             h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
             h = D.sharded_get_repr(model, blocks, model.embed(h))
             ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg)
-        return ids.cpu()
+        out = ids_pinned[:ids.shape[0]]
+        out.copy_(ids, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
 
     def barrier():
         if world > 1:
@@ -324,10 +334,12 @@ def main():
 
     def stage_ms(a, b):
         return float(np.mean([e[a].elapsed_time(e[b]) for e in rec if a in e and b in e])) if rec and a in rec[0] and b in rec[0] else None
-    stages = {'embed_in_ms': stage_ms('t0', 'embed_in'), 'aggregate_ms': stage_ms('embed_in', 'aggregate')}
-    if world == 1:
-        stages.update({'prep_ms': stage_ms('aggregate', 'score_begin'), 'score_ms': stage_ms('score_begin', 'score_end'),
-                       'rescore_ms': stage_ms('score_end', 't1')})
+    stages = {'embed_in_ms': stage_ms('t0', 'embed_in'), 'aggregate_ms': stage_ms('embed_in', 'aggregate'),
+              'prep_ms': stage_ms('aggregate', 'score_begin'), 'score_ms': stage_ms('score_begin', 'score_end'),
+              'rescore_merge_ms': stage_ms('score_end', 't1')}
+    if world > 1:
+        stages['note'] = ('rank 0; aggregate_ms includes the per-layer NCCL all-gather, '
+                          'rescore_merge_ms the all-to-all + merge')
 
     # ---- timed: end to end through the public API with host buffers
     for _ in range(min(args.warmup, 2)):
@@ -359,16 +371,19 @@ def main():
     agg_bytes *= n_conv
     roof_agg = None
     if stages.get('aggregate_ms'):
-        gbs = agg_bytes / (stages['aggregate_ms'] * 1e-3) / 1e9 * (1.0 if world == 1 else 1.0)
+        gbs = agg_bytes / world / (stages['aggregate_ms'] * 1e-3) / 1e9
+        shard_note = '' if world == 1 else ", this rank's 1/%d of the rows, all-gather time included" % world
         roof_agg = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm'],
-                    'traffic': None, 'algorithmic_bytes': agg_bytes, 'of': pk['source'],
-                    'note': 'all fused CSR gather-reduce + projection kernels of one step (4 relations); bytes = SURVEY 8d B_dst'}
+                    'traffic': DRAM_TRAFFIC.get((args.config, 'aggregate')) if world == 1 else None,
+                    'algorithmic_bytes': agg_bytes // world, 'of': pk['source'], 'per': 'GPU',
+                    'note': 'all fused CSR gather-reduce + projection kernels of one step (4 relations%s); '
+                            'bytes = SURVEY 8d B_dst' % shard_note}
     flops = 2.0 * n_users * n_items * out
     roof = None
     if stages.get('score_ms'):
-        tf = flops / (stages['score_ms'] * 1e-3) / 1e12
+        tf = flops / world / (stages['score_ms'] * 1e-3) / 1e12
         roof = {'bound': 'tensor', 'achieved': tf, 'peak': pk['tc'], 'unit': 'TFLOP/s', 'frac': tf / pk['tc'],
-                'traffic': None, 'executed_tflops': tf * (3 if args.parts == 2 else 1),
+                'traffic': DRAM_TRAFFIC.get((args.config, 'score')) if world == 1 else None, 'per': 'GPU', 'executed_tflops': tf * (3 if args.parts == 2 else 1),
                 'executed_frac': tf * (3 if args.parts == 2 else 1) / pk['tc'], 'of': pk['source'] + ' (sustained)',
                 'kernel': 'score_topk_kernel (tcgen05 %s, %d-product, fused top-%d shortlist)' % (args.elem, 3 if args.parts == 2 else 1, args.shortlist),
                 'note': 'achieved counts 2*U*I*D once; the %d-product split executes %dx that on the tensor pipe' % (3 if args.parts == 2 else 1, 3 if args.parts == 2 else 1)}

@@ -86,7 +86,8 @@ def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None) -> D
     return h
 
 
-def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought=None, config=None, group=None):
+def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought=None, config=None, group=None,
+                      mark=None):
     """Item-range-sharded scoring + owner-side merge. ``h_user`` / ``h_item`` are the full tables (every rank holds
     them after the last all-gather); ``bought`` rows follow ``h_user`` rows. Returns ``(ids [u_loc, k], scores,
     (begin, end))`` for the user range this rank owns."""
@@ -96,7 +97,7 @@ def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought
     cfg = config or RecsConfig()
     ib, ie = shard_range(h_item.shape[0], world, rank)
     table = ScoringTable(h_item[ib:ie], cfg, item_id_base=ib)
-    ids, scores = recommend_topk(h_user, table, k, bought)
+    ids, scores = recommend_topk(h_user, table, k, bought, mark=mark)
     all_ids, all_scores, ub, ue = exchange_topk(ids, scores, group)
     if world == 1:
         return ids, scores, (ub, ue)
