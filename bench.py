@@ -283,10 +283,10 @@ def main():
             h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
             h = D.sharded_get_repr(model, blocks, model.embed(h))
             ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg)
-        out = ids_pinned[:ids.shape[0]]
-        out.copy_(ids, non_blocking=True)
+        host_ids = ids_pinned[:ids.shape[0]]
+        host_ids.copy_(ids, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return out
+        return host_ids
 
     def barrier():
         if world > 1:
