@@ -253,39 +253,42 @@ __global__ void __launch_bounds__(THREADS) gather_only_kernel(const int* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ fused tile
-template <int CPL>
-__device__ __forceinline__ void load_cols(const float* __restrict__ p, float (&w)[CPL]) {
-  if (CPL == 2) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-    w[0] = v.x; w[1] = v.y;
-  } else {
-#pragma unroll
-    for (int i = 0; i < CPL / 4; ++i) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
-      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-    }
-  }
+// Projection epilogue on the tensor cores with fp32 accuracy: 3xTF32. Every fp32 operand is split into
+// hi = tf32(x) and lo = tf32(x - hi) (round-to-nearest), and z += lo.hi + hi.lo + hi.hi with fp32 accumulation
+// (mma.sync.m16n8k8.tf32): ~3 * 2^-22 relative error, i.e. indistinguishable from an fp32 FFMA GEMM at the
+// rtol 1e-4 / atol 1e-5 embedding tolerance, at a fifth of the instructions. The weights arrive pre-split and
+// pre-packed in mma B-fragment order (pack_weights_kernel), so a lane fetches both halves of a fragment with ONE
+// coalesced 128-bit load; A fragments come from the gathered tile in shared memory (row pitch D + 4: conflict-free).
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// acc[r][c] += sum_k tile[r][k] * wt[k][col0 + c] for the warp's RPW rows; tile rows have pitch dk (multiple of 4).
-template <int RPW, int CPL>
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ tile, int dk, const float* __restrict__ wt,
-                                          int d_out, int col0, float (&acc)[RPW][CPL]) {
-  for (int k = 0; k < dk; k += 4) {
-    float4 a[RPW];
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(tile + r * dk + k);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      float w[CPL];
-      load_cols<CPL>(wt + (size_t)(k + kk) * d_out + col0, w);
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) acc[r][c] = fmaf(av, w[c], acc[r][c]);
-      }
-    }
+// packed[(ks * n_tiles + nt) * 32 + lane] = {b0_hi, b1_hi, b0_lo, b1_lo} of the m16n8k8 B fragment of k-step ks
+// (8 rows of [W_self^T ; W_neigh^T]) and column tile nt: b0 = W[ks*8 + lane%4][nt*8 + lane/4], b1 = W[.. + 4][..].
+__global__ void pack_weights_kernel(const float* __restrict__ ws_t, const float* __restrict__ wn_t, int ds, int dn,
+                                    int dout, float4* __restrict__ packed) {
+  const int n_tiles = dout / 8, k_steps = (ds + dn) / 8;
+  const int total = k_steps * n_tiles * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, nt = (i >> 5) % n_tiles, ks = (i >> 5) / n_tiles;
+    const int k0 = ks * 8 + (lane & 3), n = nt * 8 + (lane >> 2);
+    auto w = [&](int k) { return k < ds ? ws_t[(size_t)k * dout + n] : wn_t[(size_t)(k - ds) * dout + n]; };
+    uint32_t h0, l0, h1, l1;
+    split_tf32(w(k0), h0, l0);
+    split_tf32(w(k0 + 4), h1, l1);
+    packed[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
   }
 }
 
@@ -298,16 +301,22 @@ struct SageParams {
   int l2norm, accumulate;
   float z_scale;
   float* out;
+  const float4* packed;  // pre-split weights in B-fragment order (fused kernel only)
 };
 
-// R = rows per tile, CPL = d_out / 32 output columns per lane, VN / VS = float4 per lane of a neighbour / self row.
-template <int VN, int VS, int CPL, int R, bool MAXR>
-__global__ void __launch_bounds__(THREADS) sage_fused_kernel(SageParams p, LongWs lw) {
+constexpr int PAD = 4;  // floats of row padding in the shared-memory tiles
+
+// MT = 16-row m-tiles per warp (tile rows R = 32 * MT: two row groups), NT = 8-column n-tiles per warp
+// (d_out = 32 * NT: four column groups). VN / VS = float4 per lane of a neighbour / self row.
+template <int VN, int VS, int NT, int MT, bool MAXR>
+__global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fused_kernel(SageParams p, LongWs lw) {
+  constexpr int R = 32 * MT;
   extern __shared__ __align__(16) float smem[];
-  float* sN = smem;                // [R][dn]
-  float* sS = smem + R * p.dn;     // [R][ds]
+  const int pn = p.dn + PAD, ps = p.ds + PAD;
+  float* sN = smem;            // [R][dn + PAD]
+  float* sS = smem + R * pn;   // [R][ds + PAD]
   __shared__ int s_next;
-  constexpr int RPW = R / WARPS;
+  __shared__ float s_part[4][R];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = p.row_begin + (int64_t)blockIdx.x * R;
   if (threadIdx.x == 0) s_next = 0;
@@ -321,60 +330,118 @@ __global__ void __launch_bounds__(THREADS) sage_fused_kernel(SageParams p, LongW
     if (r >= R) break;
     const int64_t row = row0 + r;
     if (row < p.row_end) {
-      reduce_row_to<VN, MAXR>(p.indptr, p.indices, p.ew, p.h_src, p.dn, (int)row, lane, lw, sN + r * p.dn);
+      reduce_row_to<VN, MAXR>(p.indptr, p.indices, p.ew, p.h_src, p.dn, (int)row, lane, lw, sN + r * pn);
 #pragma unroll
       for (int q = 0; q < VS; ++q) {
         const int c = (lane + 32 * q) * 4;
-        if (c < p.ds) *reinterpret_cast<float4*>(sS + r * p.ds + c) = gr::ldg_f4(p.h_dst + (size_t)row * p.ds + c);
+        if (c < p.ds) *reinterpret_cast<float4*>(sS + r * ps + c) = gr::ldg_f4(p.h_dst + (size_t)row * p.ds + c);
       }
     } else {
-      for (int c = lane * 4; c < p.dn; c += 128) *reinterpret_cast<float4*>(sN + r * p.dn + c) = make_float4(0, 0, 0, 0);
-      for (int c = lane * 4; c < p.ds; c += 128) *reinterpret_cast<float4*>(sS + r * p.ds + c) = make_float4(0, 0, 0, 0);
+      for (int c = lane * 4; c < p.dn; c += 128) *reinterpret_cast<float4*>(sN + r * pn + c) = make_float4(0, 0, 0, 0);
+      for (int c = lane * 4; c < p.ds; c += 128) *reinterpret_cast<float4*>(sS + r * ps + c) = make_float4(0, 0, 0, 0);
     }
   }
   __syncthreads();
 
-  // phase 2: z = relu(S.Ws^T + N.Wn^T); warp w owns rows [w*RPW, +RPW), lane owns columns [lane*CPL, +CPL)
-  float acc[RPW][CPL];
+  // phase 2: z = relu([S | N] . [Ws^T ; Wn^T]) on the tensor cores (3xTF32)
+  const int rg = warp & 1, cg = warp >> 1;          // row group (R / 2 rows), column group (d_out / 4 columns)
+  const int g = lane >> 2, tig = lane & 3;
+  const int n_tiles = p.dout / 8;
+  const int ks_self = p.ds / 8, ks_all = (p.ds + p.dn) / 8;
+  float acc[MT][NT][4];
 #pragma unroll
-  for (int r = 0; r < RPW; ++r)
+  for (int m = 0; m < MT; ++m)
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) acc[r][c] = 0.f;
-  const int col0 = lane * CPL;
-  tile_gemm<RPW, CPL>(sS + warp * RPW * p.ds, p.ds, p.ws_t, p.dout, col0, acc);
-  tile_gemm<RPW, CPL>(sN + warp * RPW * p.dn, p.dn, p.wn_t, p.dout, col0, acc);
-
+    for (int n = 0; n < NT; ++n)
 #pragma unroll
-  for (int r = 0; r < RPW; ++r) {
-    const int64_t row = row0 + warp * RPW + r;
-    float ss = 0.f;
+      for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
+  const float4* wp = p.packed + (size_t)(cg * NT) * 32 + lane;
+  float4 bq[NT];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      acc[r][c] = fmaxf(acc[r][c], 0.f);
-      ss = fmaf(acc[r][c], acc[r][c], ss);
+  for (int n = 0; n < NT; ++n) bq[n] = __ldg(wp + (size_t)n * 32);
+  for (int ks = 0; ks < ks_all; ++ks) {
+    float4 bcur[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) bcur[n] = bq[n];
+    if (ks + 1 < ks_all) {  // prefetch the next k-step's fragments (L1 / L2 resident)
+      const float4* nx = wp + (size_t)(ks + 1) * n_tiles * 32;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) bq[n] = __ldg(nx + (size_t)n * 32);
     }
-    if (p.l2norm) {
-      ss = gr::warp_sum(ss);
-      float nrm = sqrtf(ss);
-      if (nrm == 0.f) nrm = 1.f;
+    const float* tile = ks < ks_self ? sS : sN;
+    const int pitch = ks < ks_self ? ps : pn;
+    const int kc = (ks < ks_self ? ks : ks - ks_self) * 8 + tig;
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) acc[r][c] = acc[r][c] / nrm;
-    }
-    if (row < p.row_end) {
-      float* o = p.out + (size_t)row * p.dout + col0;
+    for (int m = 0; m < MT; ++m) {
+      const float* a = tile + (rg * (R / 2) + m * 16 + g) * pitch + kc;
+      uint32_t ah[4], al[4];
+      split_tf32(a[0], ah[0], al[0]);
+      split_tf32(a[8 * pitch], ah[1], al[1]);
+      split_tf32(a[4], ah[2], al[2]);
+      split_tf32(a[8 * pitch + 4], ah[3], al[3]);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        float z = acc[r][c];
-        if (p.accumulate == GR_ACC_ADD) z = o[c] + z;
-        else if (p.accumulate == GR_ACC_MAX) z = fmaxf(o[c], z);
-        acc[r][c] = z * p.z_scale;
+      for (int n = 0; n < NT; ++n) {
+        const uint32_t bh0 = __float_as_uint(bcur[n].x), bh1 = __float_as_uint(bcur[n].y);
+        const uint32_t bl0 = __float_as_uint(bcur[n].z), bl1 = __float_as_uint(bcur[n].w);
+        mma_tf32(acc[m][n], al, bh0, bh1);
+        mma_tf32(acc[m][n], ah, bl0, bl1);
+        mma_tf32(acc[m][n], ah, bh0, bh1);
       }
-      if (CPL == 2) {
-        *reinterpret_cast<float2*>(o) = make_float2(acc[r][0], acc[r][1]);
-      } else {
+    }
+  }
+
+  // relu + row sum of squares: a row's columns live in 4 lanes (tig) x 4 warps (cg)
+  float ss[MT][2];
 #pragma unroll
-        for (int i = 0; i < CPL / 4; ++i)
-          reinterpret_cast<float4*>(o)[i] = make_float4(acc[r][4 * i], acc[r][4 * i + 1], acc[r][4 * i + 2], acc[r][4 * i + 3]);
+  for (int m = 0; m < MT; ++m) {
+    ss[m][0] = ss[m][1] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[m][n][i] = fmaxf(acc[m][n][i], 0.f);
+        ss[m][i >> 1] = fmaf(acc[m][n][i], acc[m][n][i], ss[m][i >> 1]);
+      }
+    }
+  }
+  if (p.l2norm) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = ss[m][h];
+        v += __shfl_xor_sync(FULL, v, 1);
+        v += __shfl_xor_sync(FULL, v, 2);
+        if (tig == 0) s_part[cg][rg * (R / 2) + m * 16 + h * 8 + g] = v;
+      }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = rg * (R / 2) + m * 16 + h * 8 + g;
+      const int64_t row = row0 + r;
+      float nrm = 1.f;
+      if (p.l2norm) {
+        nrm = sqrtf((s_part[0][r] + s_part[1][r]) + (s_part[2][r] + s_part[3][r]));
+        if (nrm == 0.f) nrm = 1.f;
+      }
+      if (row < p.row_end) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          float* o = p.out + (size_t)row * p.dout + cg * (NT * 8) + n * 8 + 2 * tig;
+          float z0 = acc[m][n][2 * h], z1 = acc[m][n][2 * h + 1];
+          if (p.l2norm) { z0 = z0 / nrm; z1 = z1 / nrm; }
+          if (p.accumulate == GR_ACC_ADD) {
+            const float2 prev = *reinterpret_cast<const float2*>(o);
+            z0 = prev.x + z0; z1 = prev.y + z1;
+          } else if (p.accumulate == GR_ACC_MAX) {
+            const float2 prev = *reinterpret_cast<const float2*>(o);
+            z0 = fmaxf(prev.x, z0); z1 = fmaxf(prev.y, z1);
+          }
+          *reinterpret_cast<float2*>(o) = make_float2(z0 * p.z_scale, z1 * p.z_scale);
+        }
       }
     }
   }
@@ -482,11 +549,13 @@ int launch_long_rows(const int* indptr, const int* indices, const float* ew, con
   return GR_OK;
 }
 
-template <int VN, int VS, int CPL, int R, bool MAXR>
+template <int VN, int VS, int NT, int MT, bool MAXR>
 int launch_fused(const SageParams& p, const LongWs& lw, cudaStream_t st) {
-  const size_t smem = sizeof(float) * R * (p.dn + p.ds);
-  auto kern = sage_fused_kernel<VN, VS, CPL, R, MAXR>;
+  constexpr int R = 32 * MT;
+  const size_t smem = sizeof(float) * R * (p.dn + p.ds + 2 * PAD);
+  auto kern = sage_fused_kernel<VN, VS, NT, MT, MAXR>;
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int64_t rows = p.row_end - p.row_begin;
   const int64_t tiles = (rows + R - 1) / R;
   kern<<<(unsigned)tiles, THREADS, smem, st>>>(p, lw);
@@ -498,28 +567,30 @@ template <bool MAXR>
 int dispatch_fused(const SageParams& p, const LongWs& lw, cudaStream_t st, bool* handled) {
   *handled = true;
   const int vn = (p.dn + 127) / 128, vs = (p.ds + 127) / 128;
-#define GR_CASE(VN_, VS_, CPL_, R_) \
-  if (vn == VN_ && vs == VS_ && p.dout == 32 * CPL_) return launch_fused<VN_, VS_, CPL_, R_, MAXR>(p, lw, st);
-  GR_CASE(1, 1, 4, 64)  // 128 -> 128 (c1, c2, c5)
-  GR_CASE(1, 1, 2, 64)  // .. -> 64
-  GR_CASE(2, 2, 8, 32)  // 256 -> 256 (c3 hidden)
-  GR_CASE(2, 2, 4, 32)  // 256 -> 128 (c3 output)
-  GR_CASE(1, 1, 8, 32)  // 128 -> 256
-  GR_CASE(2, 2, 2, 32)
+#define GR_CASE(VN_, VS_, NT_, MT_) \
+  if (vn == VN_ && vs == VS_ && p.dout == 32 * NT_) return launch_fused<VN_, VS_, NT_, MT_, MAXR>(p, lw, st);
+  GR_CASE(1, 1, 4, 2)  // 128 -> 128 (c1, c2, c5): 64-row tiles
+  GR_CASE(1, 1, 2, 2)  // .. -> 64
+  GR_CASE(2, 2, 8, 1)  // 256 -> 256 (c3 hidden): 32-row tiles
+  GR_CASE(2, 2, 4, 1)  // 256 -> 128 (c3 output)
+  GR_CASE(1, 1, 8, 1)  // 128 -> 256
+  GR_CASE(2, 2, 2, 1)
 #undef GR_CASE
   *handled = false;
   return GR_OK;
 }
 
 bool fast_dims(int dn, int ds, int dout) {
-  return dn % 4 == 0 && ds % 4 == 0 && dn <= 256 && ds <= 256 && ((dn + 127) / 128 == (ds + 127) / 128) &&
+  return dn % 8 == 0 && ds % 8 == 0 && dn <= 256 && ds <= 256 && ((dn + 127) / 128 == (ds + 127) / 128) &&
          (dout == 64 || dout == 128 || dout == 256);
 }
+
+size_t packed_bytes(int dn, int ds, int dout) { return gr::align_up((size_t)(dn + ds) * dout * 2 * sizeof(float), 256); }
 
 }  // namespace
 
 extern "C" size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh) {
-  return long_ws_layout(nnz < 0 ? 0 : nnz, d_neigh, nullptr, nullptr);
+  return long_ws_layout(nnz < 0 ? 0 : nnz, d_neigh, nullptr, nullptr) + packed_bytes(256, 256, 256);
 }
 
 extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indices, const float* edge_w_or_null,
@@ -537,14 +608,22 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
   GR_REQUIRE(nnz == 0 || indices, GR_E_INVALID, "null indices");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SageParams p{indptr, indices, edge_w_or_null, h_src, h_dst, row_begin, row_end, d_neigh, d_self, d_out,
-               w_self_t, w_neigh_t, l2norm, accumulate, z_scale, out};
+               w_self_t, w_neigh_t, l2norm, accumulate, z_scale, out, nullptr};
   const bool maxr = reducer == GR_REDUCE_MAX;
   LongWs lw{};
   if (fast_dims(d_neigh, d_self, d_out)) {
-    const size_t need = long_ws_layout(nnz, d_neigh, nullptr, nullptr);
+    const size_t long_bytes = long_ws_layout(nnz, d_neigh, nullptr, nullptr);
+    const size_t need = long_bytes + packed_bytes(d_neigh, d_self, d_out);
     GR_REQUIRE(ws != nullptr && ws_bytes >= need, GR_E_WORKSPACE, "workspace too small");
     GR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, GR_E_INVALID, "workspace must be 256-byte aligned");
     long_ws_layout(nnz, d_neigh, &lw, static_cast<char*>(ws));
+    float4* packed = reinterpret_cast<float4*>(static_cast<char*>(ws) + long_bytes);
+    {
+      const int total = (d_neigh + d_self) / 8 * (d_out / 8) * 32;
+      pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, packed);
+      GR_LAUNCH_CHECK();
+      p.packed = packed;
+    }
     int rc;
     const int vn = (d_neigh + 127) / 128;
     if (maxr) rc = vn == 1 ? launch_long_rows<1, true>(indptr, indices, edge_w_or_null, h_src, d_neigh, row_begin, row_end, lw, st)
