@@ -166,13 +166,15 @@ def run_reference_arm(args, wl_name, wl):
     print(json.dumps(line))
 
 
-def workload_config(name, wl, n_gpus):
+def workload_config(name, wl, n_gpus, item_shards=None):
     n_users, n_items, n_edges, n_layers, agg, hidden, out = wl
     return {'workload': '%s: %d users x %d items x %d click/purchase edges, %d-layer ConvModel %s, hidden %d / out %d, '
                         'full-graph embeddings + top-%d recs for every user' % (name, n_users, n_items, n_edges, n_layers,
                                                                                  agg, hidden, out, K_RECS),
             'users': n_users, 'items': n_items, 'edges': n_edges, 'k': K_RECS,
-            'parallelism': 'single GPU' if n_gpus == 1 else 'dst/item id-range sharding x%d, NCCL all-gather + top-k merge' % n_gpus,
+            'parallelism': 'single GPU' if n_gpus == 1 else (
+                'dst/item id-range sharding x%d, NCCL all-gather + top-k merge' % n_gpus if item_shards != 1 else
+                'dst/user id-range sharding x%d, NCCL all-gather, replicated item table' % n_gpus),
             'l2': 'inputs larger than L2 (CSR + tables >> 126 MB per step), no explicit flush'}
 
 
@@ -187,6 +189,7 @@ def main():
     ap.add_argument('--elem', default='bf16', choices=['bf16', 'fp16'])
     ap.add_argument('--parts', type=int, default=2, choices=[1, 2])
     ap.add_argument('--shortlist', type=int, default=16)
+    ap.add_argument('--item-shards', type=int, default=None, help='N>1: item-range shards (default = world, the north-star layout); 1 = user-range sharding with a replicated item table')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true')
     args = ap.parse_args()
@@ -263,7 +266,7 @@ def main():
             ids, scores, n_over = grb.recommend_topk(h['user'], table, K_RECS, bought, return_overflow=True, mark=mark)
         else:
             mark('prep0')
-            ids, scores, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark)
+            ids, scores, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark, item_shards=args.item_shards)
             n_over = torch.zeros(1, dtype=torch.int32, device=dev)
         mark('t1')
         if record is not None:
@@ -282,7 +285,7 @@ def main():
         else:
             h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
             h = D.sharded_get_repr(model, blocks, model.embed(h))
-            ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg)
+            ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, item_shards=args.item_shards)
         host_ids = ids_pinned[:ids.shape[0]]
         host_ids.copy_(ids, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -398,7 +401,7 @@ def main():
         'metric': 'users/sec for full-graph embed+top-10 recs', 'value': value, 'unit': 'users/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 embeddings + %s%s scoring (f32 accumulate, f32 re-score)' % (args.elem, 'x3' if args.parts == 2 else ''),
-        'data': 'synthetic', 'config': workload_config(args.config, wl, world),
+        'data': 'synthetic', 'config': workload_config(args.config, wl, world, args.item_shards),
         'e2e': {'value': n_users / e2e_s, 'unit': 'users/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_aggregation': roof_agg,

@@ -87,14 +87,29 @@ def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None) -> D
 
 
 def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought=None, config=None, group=None,
-                      mark=None):
-    """Item-range-sharded scoring + owner-side merge. ``h_user`` / ``h_item`` are the full tables (every rank holds
-    them after the last all-gather); ``bought`` rows follow ``h_user`` rows. Returns ``(ids [u_loc, k], scores,
-    (begin, end))`` for the user range this rank owns."""
+                      mark=None, item_shards: Optional[int] = None):
+    """Sharded scoring. ``h_user`` / ``h_item`` are the full tables (every rank holds them after the last
+    all-gather); ``bought`` rows follow ``h_user`` rows. Returns ``(ids [u_loc, k], scores, (begin, end))`` for the
+    user range this rank owns.
+
+    ``item_shards = world`` (default, the layout the north star prescribes): the item table is cut into ``world``
+    contiguous id ranges, every rank scores ALL users against its range and the per-shard exact top-k lists are
+    merged on the rank owning the user range. ``item_shards = 1``: the cross-check layout -- every rank scores only
+    its own user range against the whole (replicated) item table, no exchange; cheaper when users >> items because
+    the per-user prep / re-score work is not repeated on every rank."""
     from . import ops
     from .recs import RecsConfig, ScoringTable, recommend_topk
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     cfg = config or RecsConfig()
+    item_shards = world if item_shards is None else item_shards
+    if item_shards == 1 and world > 1:
+        ub, ue = shard_range(h_user.shape[0], world, rank)
+        table = ScoringTable(h_item, cfg)
+        sub = None if bought is None else bought.select(range(ub, ue))
+        ids, scores = recommend_topk(h_user[ub:ue], table, k, sub, mark=mark)
+        return ids, scores, (ub, ue)
+    if item_shards != world:
+        raise ValueError('item_shards must be 1 or the world size')
     ib, ie = shard_range(h_item.shape[0], world, rank)
     table = ScoringTable(h_item[ib:ie], cfg, item_id_base=ib)
     ids, scores = recommend_topk(h_user, table, k, bought, mark=mark)

@@ -178,3 +178,19 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_dst: int):
     N.call('gr_csr_build_i32', N.ptr(src), N.ptr(dst), nnz, n_dst, N.ptr(indptr), N.ptr(indices), N.ptr(eperm),
            N.ptr(ws), ws.numel(), N.stream())
     return indptr, indices, eperm
+
+
+def remap_first_appearance(raw: torch.Tensor):
+    """Raw int64 ids -> ``(new_ids int32 [n], uniq_raw int64 [n_unique])``: contiguous ids in order of first
+    appearance (``create_ids``, reference ``src/builder.py:182-227``)."""
+    assert raw.dtype == torch.int64
+    n = int(raw.shape[0])
+    dev = raw.device
+    new_ids = torch.empty(n, dtype=torch.int32, device=dev)
+    uniq = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = N.load()
+    ws = N.workspace(lib.gr_remap_workspace_bytes(n), dev)
+    N.call('gr_remap_first_appearance_i64', N.ptr(raw), n, N.ptr(new_ids), N.ptr(uniq), N.ptr(n_unique), N.ptr(ws),
+           ws.numel(), N.stream())
+    return new_ids, uniq[:int(n_unique.item())]

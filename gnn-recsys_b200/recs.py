@@ -91,6 +91,9 @@ class BoughtCSR:
 
     def select(self, user_ids) -> 'BoughtCSR':
         """Rows re-ordered to follow ``user_ids`` (vectorised)."""
+        if isinstance(user_ids, range) and self._row_of_user is None and user_ids.step == 1:
+            lo, hi = user_ids.start, user_ids.stop  # contiguous slice: no gather
+            return BoughtCSR(self.indptr[lo:hi + 1] - self.indptr[lo], self.ids[self.indptr[lo]:self.indptr[hi]])
         uid = np.asarray(user_ids, dtype=np.int64).reshape(-1)
         if self._row_of_user is not None:
             uid = np.asarray([self._row_of_user[int(u)] for u in uid], dtype=np.int64)

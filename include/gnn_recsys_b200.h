@@ -141,6 +141,14 @@ size_t gr_csr_build_workspace_bytes(int64_t nnz, int32_t n_dst);
 int gr_csr_build_i32(const int32_t* src, const int32_t* dst, int64_t nnz, int32_t n_dst, int32_t* indptr,
                      int32_t* indices, int32_t* eperm, void* ws, size_t ws_bytes, gr_stream_t stream);
 
+/* ---- ID remap next to the path: raw ids -> contiguous ids in order of FIRST APPEARANCE,
+ *      replacing create_ids (src/builder.py:182-227: pandas unique() order + merge). new_ids[i] in [0, *n_unique);
+ *      uniq_raw[new id] = raw id (optional reverse map, capacity n); n_unique is a device int32. INT64_MIN is not a
+ *      valid raw id. Deterministic (hash table keeps the smallest position per id) and bit-exact vs the CPU rule. */
+size_t gr_remap_workspace_bytes(int64_t n);
+int gr_remap_first_appearance_i64(const int64_t* raw, int64_t n, int32_t* new_ids, int64_t* uniq_raw_or_null,
+                                  int32_t* n_unique, void* ws, size_t ws_bytes, gr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ def main():
         b = (hu.unsqueeze(1) * hi[ids_s.long().clamp(min=0)]).sum(-1)
         assert bool(((a - b).abs() < 1e-5).all()), 'sharded top-k differs beyond score ties (%s)' % agg
         assert bool(((ids1[ub:ue] < 0) == (ids_s < 0)).all())
+        ids_u, sc_u, (vb, ve) = D.sharded_recommend(hs['user'], hs['item'], 10, bought, item_shards=1)
+        assert (vb, ve) == (ub, ue) and torch.equal(ids_u, ids1[ub:ue]), 'user-sharded layout differs (%s)' % agg
         same = float((ids1[ub:ue] == ids_s).float().mean())
         if rank == 0:
             print('multi-gpu check ok: world=%d agg=%s identical ids %.4f (rest are ties < 1e-5)' % (world, agg, same))

@@ -19,7 +19,7 @@ def test_header_declares_the_whole_path():
     names = declared_symbols()
     for must in ('gr_linear_f32', 'gr_sage_relation_f32', 'gr_gather_reduce_f32', 'gr_edge_cosine_f32', 'gr_score_prep',
                  'gr_score_topk_tc', 'gr_rescore_topk_f32', 'gr_score_topk_exact_f32', 'gr_topk_merge',
-                 'gr_csr_build_i32', 'gr_last_error'):
+                 'gr_csr_build_i32', 'gr_remap_first_appearance_i64', 'gr_last_error'):
         assert must in names
 
 

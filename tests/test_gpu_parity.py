@@ -268,6 +268,25 @@ def test_csr_build_bit_exact(grb, shape):
         assert np.array_equal(w_indptr, o_indptr) and np.array_equal(w_indices, o_indices) and np.array_equal(w_eperm, o_eperm)
 
 
+@pytest.mark.parametrize('n,span', [(0, 10), (1, 1), (5000, 300), (2_000_000, 150_000), (100_000, 10 ** 15)])
+def test_id_remap_bit_exact(grb, n, span):
+    """create_ids (src/builder.py:182-227): contiguous ids in order of first appearance, bit-exact."""
+    rng = np.random.default_rng(n + 7)
+    raw = (rng.integers(0, span, n) - span // 3).astype(np.int64)  # negative raw ids too
+    new_ids, uniq = grb.ops.remap_first_appearance(torch.from_numpy(raw).cuda())
+    _, first = np.unique(raw, return_index=True)
+    want_uniq = raw[np.sort(first)]
+    lookup = {int(r): i for i, r in enumerate(want_uniq.tolist())} if n <= 5000 else None
+    assert np.array_equal(uniq.cpu().numpy(), want_uniq)
+    if n:
+        order = np.argsort(want_uniq, kind='stable')
+        want_ids = order[np.searchsorted(want_uniq[order], raw)].astype(np.int32)
+        assert np.array_equal(new_ids.cpu().numpy(), want_ids)
+    if lookup is not None and n:
+        o_ids, o_uniq = O.first_appearance_ids(raw.tolist())
+        assert np.array_equal(new_ids.cpu().numpy(), o_ids.astype(np.int32)) and o_uniq == want_uniq.tolist()
+
+
 def test_topk_merge_vs_oracle(grb):
     rng = np.random.default_rng(3)
     parts, n, k_in, k_out = 5, 300, 16, 10
