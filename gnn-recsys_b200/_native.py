@@ -29,7 +29,8 @@ SIGNATURES = {
     'gr_version': (C.c_int, []),
     'gr_launch_count': (C.c_longlong, []),
     'gr_device_info': (C.c_int, [_vp, _vp, _vp]),
-    'gr_linear_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, C.c_int, _vp, _vp]),
+    'gr_linear_workspace_bytes': (_sz, [_i32, _i32]),
+    'gr_linear_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, C.c_int, _vp, _vp, _sz, _vp]),
     'gr_sage_relation_workspace_bytes': (_sz, [_i64, _i32]),
     'gr_sage_relation_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _i32, C.c_int,
                                        C.c_int, C.c_int, _f32, _vp, _vp, _sz, _vp]),
@@ -44,8 +45,10 @@ SIGNATURES = {
                                    _vp]),
     'gr_rescore_topk_f32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _vp, _f32, _f32, _f32, _i32,
                                       _f32, _vp, _vp, _vp, _vp, _vp]),
-    'gr_score_topk_exact_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _f32, _vp, _vp,
-                                          _vp]),
+    'gr_score_topk_exact_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _f32, _vp, _f32,
+                                          _vp, _vp, _vp]),
+    'gr_metrics_workspace_bytes': (_sz, [_i64]),
+    'gr_metrics_at_k': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gr_topk_merge': (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gr_csr_build_workspace_bytes': (_sz, [_i64, _i32]),
     'gr_csr_build_i32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
     const float* __restrict__ hu, const int* __restrict__ user_list, const int* __restrict__ n_list, long long n_users,
     const float* __restrict__ hi, long long n_items, long long item_id_base, int d,
     const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int k, float eps,
-    int* __restrict__ out_ids, float* __restrict__ out_scores) {
+    const float* __restrict__ popularity, float weight_popularity, int* __restrict__ out_ids,
+    float* __restrict__ out_scores) {
   extern __shared__ __align__(16) float smem[];
   float* xu = smem;                                            // [d_al]
   const int d_al = (d + 3) & ~3;
@@ -247,11 +248,31 @@ __global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
     const float nu = s_nu;
     long long b0 = 0, b1 = 0;
     if (bought_indptr != nullptr) { b0 = bought_indptr[u]; b1 = bought_indptr[u + 1]; }
+    // popularity re-rank (src/metrics.py:69-72): rating = softmax_i(cos) + w * popularity_i. Pass 1: the softmax
+    // denominator Z = sum_i exp(cos_i - 1) (cos <= 1, so the shift plays the role of the reference's max)
+    float inv_z = 0.f;
+    if (popularity != nullptr) {
+      float z = 0.f;
+      for (long long i = tid; i < n_items; i += EX_THREADS) {
+        float dot, ni;
+        dot_norm(xu, hi + i * d, d, dot, ni);
+        z += expf(cosine(dot, nu, ni, eps) - 1.f);
+      }
+      z = gr::warp_sum(z);
+      __syncthreads();
+      if (lane == 0) red_s[w] = z;
+      __syncthreads();
+      float a = 0.f;
+      for (int i = 0; i < EX_THREADS / 32; ++i) a += red_s[i];
+      inv_z = 1.f / a;
+      __syncthreads();
+    }
     float tau = -INFINITY;
     for (long long i = tid; i < n_items; i += EX_THREADS) {
       float dot, ni;
       dot_norm(xu, hi + i * d, d, dot, ni);
-      const float s = cosine(dot, nu, ni, eps);
+      float s = cosine(dot, nu, ni, eps);
+      if (popularity != nullptr) s = fmaf(weight_popularity, __ldg(popularity + i), expf(s - 1.f) * inv_z);
       if (s > tau) {
         const int gid = (int)(item_id_base + i);
         long long lo = b0, hi_ = b1;
@@ -343,7 +364,84 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ metrics@k
+// recs_to_metrics (src/metrics.py:81-107) as counters: [0] recommended ids, [1] of those in the user's ground truth,
+// [2] ground-truth entries (duplicates kept), [3] of those recommended, [4] distinct recommended items.
+__global__ void __launch_bounds__(256) metrics_kernel(const int* __restrict__ recs, long long n_users, int k,
+                                                      const long long* __restrict__ t_indptr,
+                                                      const int* __restrict__ t_ids, unsigned int* __restrict__ bitmap,
+                                                      unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (long long u = warp; u < n_users; u += n_warps) {
+    const long long b0 = t_indptr[u], b1 = t_indptr[u + 1];
+    const int id = lane < k ? recs[u * k + lane] : -1;
+    if (id >= 0) {
+      ++c0;
+      long long lo = b0, hi = b1;
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (t_ids[mid] < id) lo = mid + 1; else hi = mid;
+      }
+      if (lo < b1 && t_ids[lo] == id) ++c1;
+      atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+    }
+    for (long long j = b0 + lane; j < ((b1 - b0 + 31) / 32) * 32 + b0; j += 32) {
+      const int t = j < b1 ? t_ids[j] : -2;
+      bool hit = false;
+      for (int i = 0; i < k; ++i) hit |= (__shfl_sync(FULL, id, i) == t);
+      if (j < b1) { ++c2; if (hit) ++c3; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(FULL, c0, o); c1 += __shfl_xor_sync(FULL, c1, o);
+    c2 += __shfl_xor_sync(FULL, c2, o); c3 += __shfl_xor_sync(FULL, c3, o);
+  }
+  if (lane == 0) {
+    atomicAdd(counters + 0, c0); atomicAdd(counters + 1, c1); atomicAdd(counters + 2, c2); atomicAdd(counters + 3, c3);
+  }
+}
+
+__global__ void popcount_kernel(const unsigned int* __restrict__ bitmap, long long n_words,
+                                unsigned long long* __restrict__ counters) {
+  unsigned long long c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_words; i += (long long)gridDim.x * blockDim.x)
+    c += __popc(bitmap[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counters + 4, c);
+}
+
 }  // namespace
+
+extern "C" size_t gr_metrics_workspace_bytes(int64_t n_items) {
+  return gr::align_up((size_t)((n_items + 31) / 32) * 4 + 4, 256);
+}
+
+extern "C" int gr_metrics_at_k(const int32_t* recs, int64_t n_users, int32_t k, const int64_t* truth_indptr,
+                               const int32_t* truth_ids, int64_t n_items, uint64_t* counters5, void* ws,
+                               size_t ws_bytes, gr_stream_t stream) {
+  GR_REQUIRE(n_users >= 0 && k >= 1 && k <= 32 && n_items >= 0, GR_E_INVALID, "bad shape (k must be in [1, 32])");
+  GR_REQUIRE(counters5 != nullptr, GR_E_INVALID, "null counters");
+  GR_REQUIRE(ws != nullptr && ws_bytes >= gr_metrics_workspace_bytes(n_items), GR_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n_words = (n_items + 31) / 32;
+  GR_CUDA(cudaMemsetAsync(counters5, 0, 5 * sizeof(uint64_t), st));
+  GR_CUDA(cudaMemsetAsync(ws, 0, (size_t)n_words * 4 + 4, st));
+  if (n_users == 0) return GR_OK;
+  GR_REQUIRE(recs && truth_indptr && truth_ids, GR_E_INVALID, "null pointer");
+  const int grid = (int)std::min<int64_t>((n_users + 7) / 8, (int64_t)gr::sm_count() * 16);
+  metrics_kernel<<<grid, 256, 0, st>>>(recs, n_users, k, reinterpret_cast<const long long*>(truth_indptr), truth_ids,
+                                       static_cast<unsigned int*>(ws), reinterpret_cast<unsigned long long*>(counters5));
+  GR_LAUNCH_CHECK();
+  popcount_kernel<<<std::max(1, (int)std::min<long long>((n_words + 255) / 256, gr::sm_count() * 8)), 256, 0, st>>>(
+      static_cast<unsigned int*>(ws), n_words, reinterpret_cast<unsigned long long*>(counters5));
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}
 
 extern "C" size_t gr_colmean_workspace_bytes(int64_t n, int32_t d) {
   (void)n;
@@ -409,7 +507,8 @@ extern "C" int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_
                                        const int32_t* n_list_or_null, int64_t n_users, const float* h_item,
                                        int64_t n_items, int64_t item_id_base, int32_t d,
                                        const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null,
-                                       int32_t k, float eps, int32_t* out_ids, float* out_scores, gr_stream_t stream) {
+                                       int32_t k, float eps, const float* popularity_or_null, float weight_popularity,
+                                       int32_t* out_ids, float* out_scores, gr_stream_t stream) {
   GR_REQUIRE(n_users >= 0 && n_items >= 0 && d > 0 && d <= 4096, GR_E_INVALID, "bad shape");
   GR_REQUIRE(k >= 1 && k <= 32, GR_E_INVALID, "k must be in [1, 32]");
   GR_REQUIRE(item_id_base >= 0 && item_id_base + n_items <= 0x7fffffffLL, GR_E_INVALID, "item ids must fit int32");
@@ -423,7 +522,8 @@ extern "C" int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_
   const int grid = (int)std::min<int64_t>(n_users, (int64_t)gr::sm_count() * 8);
   exact_topk_kernel<<<grid, EX_THREADS, smem, st>>>(
       h_user, user_list_or_null, n_list_or_null, n_users, h_item, n_items, item_id_base, d,
-      reinterpret_cast<const long long*>(bought_indptr_or_null), bought_ids_or_null, k, eps, out_ids, out_scores);
+      reinterpret_cast<const long long*>(bought_indptr_or_null), bought_ids_or_null, k, eps, popularity_or_null,
+      weight_popularity, out_ids, out_scores);
   GR_LAUNCH_CHECK();
   return GR_OK;
 }

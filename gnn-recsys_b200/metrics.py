@@ -43,7 +43,7 @@ def _device_of(h, device):
 @torch.no_grad()
 def get_recs_tensor(g, h, k, user_ids, already_bought=None, remove_already_bought=True, device=None,
                     config: Optional[RecsConfig] = None, table: Optional[ScoringTable] = None,
-                    return_scores: bool = False):
+                    return_scores: bool = False, use_popularity: bool = False, weight_popularity=1):
     """``[len(user_ids), k]`` int32 item ids on the device (``-1`` where fewer than k items qualify)."""
     dev = _device_of(h, device)
     cfg = config or RecsConfig()
@@ -63,7 +63,10 @@ def get_recs_tensor(g, h, k, user_ids, already_bought=None, remove_already_bough
             bought = already_bought.select(uid)
         else:
             bought = BoughtCSR.from_dict(already_bought, uid.tolist())
-    ids, scores = recommend_topk(hu, table, k, bought)
+    pop = None
+    if use_popularity:  # g.ndata['popularity']['item'] like the reference (src/metrics.py:71)
+        pop = g.nodes['item'].data['popularity'].to(dev, torch.float32).reshape(-1).contiguous()
+    ids, scores = recommend_topk(hu, table, k, bought, popularity=pop, weight_popularity=float(weight_popularity))
     return (ids, scores) if return_scores else ids
 
 
@@ -74,10 +77,9 @@ def get_recs(g, h, model, embed_dim, k, user_ids, already_bought_dict, remove_al
         raise NotImplementedError("pred='nn' (MLP scorer) is outside the accelerated hot path (DESIGN.md, scope)")
     if pred != 'cos':
         raise KeyError(f'Prediction function {pred} not recognized.')
-    if use_popularity:
-        raise NotImplementedError('use_popularity re-ranking is not implemented yet (DESIGN.md, next)')
     print('Computing recommendations on {} users, for {} items'.format(len(user_ids), g.num_nodes('item')))
-    ids = get_recs_tensor(g, h, k, user_ids, already_bought_dict, remove_already_bought, device).cpu().numpy()
+    ids = get_recs_tensor(g, h, k, user_ids, already_bought_dict, remove_already_bought, device,
+                          use_popularity=use_popularity, weight_popularity=weight_popularity).cpu().numpy()
     ids = ids.astype(np.int64)
     recs = {}
     for r, user in enumerate(user_ids):
@@ -85,3 +87,53 @@ def get_recs(g, h, model, embed_dim, k, user_ids, already_bought_dict, remove_al
         row = row[row >= 0]
         recs[user] = list(row) if remove_already_bought else row
     return recs
+
+
+def create_ground_truth(users, items):
+    """Dictionary user id -> item ids the user actually bought (reference ``src/metrics.py:8-16``)."""
+    ground_truth_dict = defaultdict(list)
+    for key, val in zip(np.asarray(users).tolist(), np.asarray(items).tolist()):
+        ground_truth_dict[key].append(val)
+    return ground_truth_dict
+
+
+def metrics_from_tensor(ids: torch.Tensor, truth: BoughtCSR, n_items: int):
+    """precision, recall, coverage of an ``[n, k]`` id table against a ground-truth CSR whose rows follow the rows
+    of ``ids`` -- ``recs_to_metrics`` (reference ``src/metrics.py:81-107``) computed on the device."""
+    from . import ops
+    tptr, tids = truth.on(ids.device)
+    c = ops.metrics_at_k(ids.contiguous(), tptr, tids, n_items).cpu().tolist()
+    return c[1] / c[0], c[3] / c[2], c[4] / n_items
+
+
+def recs_to_metrics(recs, ground_truth_dict, g):
+    """Given the recommendations and the ground truth, computes precision, recall & coverage (dict API of the
+    reference; the counting runs on the device)."""
+    users = list(recs.keys())
+    k = max((len(v) for v in recs.values()), default=1)
+    ids = np.full((len(users), max(k, 1)), -1, dtype=np.int32)
+    for r, u in enumerate(users):
+        row = np.asarray(recs[u], dtype=np.int32)
+        ids[r, :row.size] = row
+    truth = BoughtCSR.from_dict(ground_truth_dict, users)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    return metrics_from_tensor(torch.from_numpy(ids).to(dev), truth, g.num_nodes('item'))
+
+
+def get_metrics_at_k(h, g, model, embed_dim, ground_truth, bought_eids, k, remove_already_bought=True, cuda=False,
+                     device=None, pred='cos', use_popularity=False, weight_popularity=1):
+    """create already_bought & ground truth, get recs and compute metrics (reference ``src/metrics.py:110-134``),
+    without the Python dicts in between."""
+    if pred == 'nn':
+        raise NotImplementedError("pred='nn' (MLP scorer) is outside the accelerated hot path (DESIGN.md, scope)")
+    if pred != 'cos':
+        raise KeyError(f'Prediction function {pred} not recognized.')
+    users, items = ground_truth
+    users, items = np.asarray(users), np.asarray(items)
+    user_ids = np.unique(users)
+    n_users = g.num_nodes('user')
+    bought = create_already_bought_csr(g, bought_eids) if remove_already_bought else None
+    truth = BoughtCSR.from_edges(users, items, n_users).select(user_ids)
+    ids = get_recs_tensor(g, h, k, user_ids, bought, remove_already_bought, device, use_popularity=use_popularity,
+                          weight_popularity=weight_popularity)
+    return metrics_from_tensor(ids, truth, g.num_nodes('item'))

@@ -37,8 +37,9 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = Non
     d_out = wt.shape[1]
     assert wt.shape[0] == d_in
     y = torch.empty((n, d_out), dtype=torch.float32, device=x.device)
+    ws = _ws(N.load().gr_linear_workspace_bytes(d_in, d_out), x.device, 'linear')
     N.call('gr_linear_f32', N.ptr(x), n, d_in, N.ptr(wt), N.ptr(_f32(bias)) if bias is not None else None, d_out,
-           int(relu), N.ptr(y), N.stream())
+           int(relu), N.ptr(y), N.ptr(ws), ws.numel(), N.stream())
     return y
 
 
@@ -138,7 +139,8 @@ def rescore_topk(h_user, h_item, item_id_base: int, center, sl_score, sl_id, sta
 
 
 def score_topk_exact(h_user, h_item, item_id_base: int, bought_indptr, bought_ids, k: int, eps: float,
-                     user_list=None, n_list=None, out_ids=None, out_scores=None):
+                     user_list=None, n_list=None, out_ids=None, out_scores=None, popularity=None,
+                     weight_popularity: float = 1.0):
     """Exact fp32 top-k for the listed users (all users when ``user_list`` is None), written in place into
     ``out_ids`` / ``out_scores`` rows of those users."""
     n_users, d = h_user.shape
@@ -149,9 +151,21 @@ def score_topk_exact(h_user, h_item, item_id_base: int, bought_indptr, bought_id
     N.call('gr_score_topk_exact_f32', N.ptr(h_user), N.ptr(user_list) if user_list is not None else None,
            N.ptr(n_list) if n_list is not None else None, n_users, N.ptr(h_item), h_item.shape[0], item_id_base, d,
            N.ptr(bought_indptr) if bought_indptr is not None else None,
-           N.ptr(bought_ids) if bought_ids is not None else None, k, eps, N.ptr(out_ids), N.ptr(out_scores),
-           N.stream())
+           N.ptr(bought_ids) if bought_ids is not None else None, k, eps,
+           N.ptr(popularity) if popularity is not None else None, float(weight_popularity), N.ptr(out_ids),
+           N.ptr(out_scores), N.stream())
     return out_ids, out_scores
+
+
+def metrics_at_k(recs: torch.Tensor, truth_indptr: torch.Tensor, truth_ids: torch.Tensor, n_items: int) -> torch.Tensor:
+    """Counters of ``recs_to_metrics`` (see include/gnn_recsys_b200.h): uint64[5] on the device (as int64)."""
+    n_users, k = recs.shape
+    dev = recs.device
+    counters = torch.zeros(5, dtype=torch.int64, device=dev)
+    ws = _ws(N.load().gr_metrics_workspace_bytes(n_items), dev, 'metrics')
+    N.call('gr_metrics_at_k', N.ptr(recs), n_users, k, N.ptr(truth_indptr), N.ptr(truth_ids), n_items, N.ptr(counters),
+           N.ptr(ws), ws.numel(), N.stream())
+    return counters
 
 
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int):

@@ -135,7 +135,8 @@ class ScoringTable:
 
 
 def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Optional[BoughtCSR] = None,
-                   return_overflow: bool = False, mark=None):
+                   return_overflow: bool = False, mark=None, popularity: Optional[torch.Tensor] = None,
+                   weight_popularity: float = 1.0):
     """Top-``k`` items of ``table`` for every row of ``h_user`` (``[n, d]`` fp32, CUDA): ``(ids int32 [n, k],
     scores fp32 [n, k])`` sorted by (score desc, id asc); ``-1`` / ``-inf`` pad rows with fewer than k candidates.
     ``bought`` rows must follow ``h_user`` rows. ids are global (``table.item_id_base`` added).
@@ -148,8 +149,10 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
     bptr, bids = (None, None) if bought is None else bought.on(dev)
     if bought is not None and bought.n_rows != n:
         raise ValueError('bought rows (%d) do not match user rows (%d)' % (bought.n_rows, n))
-    if not table.tc:
-        ids, scores = ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS)
+    if popularity is not None or not table.tc:
+        # popularity re-rank (softmax over ALL items + w * popularity) runs on the exact fp32 kernel only
+        ids, scores = ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS,
+                                           popularity=popularity, weight_popularity=weight_popularity)
         return (ids, scores, torch.zeros(1, dtype=torch.int32, device=dev)) if return_overflow else (ids, scores)
     shortlist = max(cfg.shortlist, k)
     if shortlist > 32:

@@ -47,9 +47,12 @@ int gr_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 /* ---- a1 NodeEmbedding.forward (src/model.py:19-24, nn.Linear with bias) and the pre-aggregation projection
  *      relu(fc_preagg(h)) of mean_nn / pool_nn (src/model.py:151,158; bias-free). Replaces torch addmm / cuBLAS sgemm.
  *      y[n, d_out] = x[n, d_in] . wt[d_in, d_out] (+ bias) (relu).  `wt` is the nn.Linear weight TRANSPOSED
- *      (k-major) so that output columns are contiguous.  fp32 FFMA accumulation in k order. */
+ *      (k-major) so that output columns are contiguous. d_in <= 8: fp32 FFMA stream; d_in % 8 == 0 and d_out % 32 == 0
+ *      with a workspace: 3xTF32 tensor-core GEMM (hi/lo split of both operands, fp32 accumulate: fp32-accurate);
+ *      anything else: fp32 FFMA SGEMM. ws (gr_linear_workspace_bytes, 16-byte aligned) may be NULL (FFMA path). */
+size_t gr_linear_workspace_bytes(int32_t d_in, int32_t d_out);
 int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const float* wt, const float* bias_or_null,
-                  int32_t d_out, int relu, float* y, gr_stream_t stream);
+                  int32_t d_out, int relu, float* y, void* ws, size_t ws_bytes, gr_stream_t stream);
 
 /* ---- a3-a6 ConvLayer.forward for one relation, fused (src/model.py:123-237), replacing DGL update_all
  *      (libdgl SpMM copy_u/u_mul_e + mean/max), two torch sgemm, relu, norm/where/div and HeteroGraphConv's
@@ -104,7 +107,9 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *           which kth_exact < that bound - tie_tol are appended to overflow_users / n_overflow (caller zero-initialises
  *           n_overflow) and must be recomputed by stage 3.
  *  stage 3  gr_score_topk_exact_f32: exact fp32 scoring of all items for the listed users (the overflow list, or
- *           every user when user_list == NULL): the always-correct fallback and the brute-force checker.
+ *           every user when user_list == NULL): the always-correct fallback and the brute-force checker. With
+ *           popularity != NULL it ranks by softmax_i(cos) + weight * popularity_i instead (use_popularity branch of
+ *           get_recs, src/metrics.py:69-72; popularity[i] belongs to local item i), two passes over the items.
  *  merge    gr_topk_merge: row-wise merge of `parts` partial (score desc, id) lists into the k_out best
  *           (scores[p][u][k_in]); ties by smaller id; ids < 0 are empty slots. */
 enum { GR_ELEM_BF16 = 0, GR_ELEM_FP16 = 1 };
@@ -128,9 +133,20 @@ int gr_rescore_topk_f32(const float* h_user, const float* h_item, int64_t item_i
 int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_list_or_null, const int32_t* n_list_or_null,
                             int64_t n_users, const float* h_item, int64_t n_items, int64_t item_id_base, int32_t d,
                             const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t k,
-                            float eps, int32_t* out_ids, float* out_scores, gr_stream_t stream);
+                            float eps, const float* popularity_or_null, float weight_popularity, int32_t* out_ids,
+                            float* out_scores, gr_stream_t stream);
 int gr_topk_merge(const float* scores, const int32_t* ids, int32_t parts, int64_t n_users, int32_t k_in,
                   int32_t k_out, float* out_scores, int32_t* out_ids, gr_stream_t stream);
+
+/* ---- metrics@k next to the path: recs_to_metrics (src/metrics.py:81-107) as counters.
+ *      recs[n_users][k] (-1 = empty), ground truth as a CSR per user (int64 indptr, int32 ids sorted ascending,
+ *      duplicates kept). counters5 (device uint64[5]): [0] recommended ids, [1] of those in the ground truth
+ *      (precision = [1]/[0]), [2] ground-truth entries, [3] of those recommended (recall = [3]/[2]), [4] distinct
+ *      recommended items (coverage = [4]/n_items). */
+size_t gr_metrics_workspace_bytes(int64_t n_items);
+int gr_metrics_at_k(const int32_t* recs, int64_t n_users, int32_t k, const int64_t* truth_indptr,
+                    const int32_t* truth_ids, int64_t n_items, uint64_t* counters5, void* ws, size_t ws_bytes,
+                    gr_stream_t stream);
 
 /* ---- graph ingest next to the path: stable COO -> int32 CSR over destination rows on the
  *      device, replacing what dgl.heterograph (src/builder.py:377-383) + DGL's lazy CSC build behind update_all do on

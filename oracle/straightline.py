@@ -225,7 +225,14 @@ def cosine_scores(user_emb, item_emb, eps=1e-6):
     return w12 / torch.sqrt(torch.clamp(w1 * w2, min=eps * eps))
 
 
-def get_recs(h_user, h_item, k, user_ids, already_bought, remove_already_bought=True):
+def softmax(x):
+    """src/utils.py:53-58."""
+    e_x = np.exp(x - np.max(x))
+    return e_x / e_x.sum()
+
+
+def get_recs(h_user, h_item, k, user_ids, already_bought, remove_already_bought=True, popularity=None,
+             weight_popularity=1):
     """src/metrics.py:52-77, one user at a time like the reference: repeat the user row, cosine against every
     item, ``np.argsort(-ratings)``, Python filter of already-bought ids, first k."""
     n_items, dim = h_item.shape
@@ -236,11 +243,23 @@ def get_recs(h_user, h_item, k, user_ids, already_bought, remove_already_bought=
         rpt = torch.cat(n_items * [user_emb]).reshape(-1, dim)                       # metrics.py:55
         ratings = torch.nn.CosineSimilarity(dim=1, eps=1e-6)(rpt, h_item)            # metrics.py:58-59
         ratings = ratings.cpu().detach().numpy().reshape(n_items, )
+        if popularity is not None:                                                    # metrics.py:69-72
+            ratings = np.add(softmax(ratings), np.asarray(popularity).reshape(n_items, ) * weight_popularity)
         order = np.argsort(-ratings)                                                  # metrics.py:73
         if remove_already_bought:
             order = [item for item in order if item not in bought]                   # metrics.py:75
         recs[user] = order[:k]
     return recs
+
+
+def recs_to_metrics(recs, ground_truth, n_items):
+    """src/metrics.py:81-107: precision, recall (ground-truth duplicates counted), coverage."""
+    k_rel = sum(len([i for i in iids if i in ground_truth[u]]) for u, iids in recs.items())
+    k_tot = sum(len(iids) for iids in recs.values())
+    r_rel = sum(len([i for i in ground_truth[u] if i in iids]) for u, iids in recs.items())
+    r_tot = sum(len(ground_truth[u]) for u in recs)
+    cov = len(set(i for iids in recs.values() for i in iids)) / n_items
+    return k_rel / k_tot, r_rel / r_tot, cov
 
 
 def get_recs_scores(h_user, h_item, user_ids):

@@ -201,5 +201,39 @@ def main():
     forward_case('fwd_fanout_mean', 300, 120, 5000, seed=11, hidden=32, out=16, fanouts=[10, 10], batch=64, neg_k=20)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+
+
+def popularity_case(base_name, weight, seed):
+    """use_popularity branch of the reference's get_recs (src/metrics.py:69-72) on the embeddings of an existing
+    fixture: item popularity = share of purchases (like src/builder.py:472-491 a [I, 1] float tensor)."""
+    z = np.load(os.path.join(HERE, base_name + '.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    n_users, n_items, k = meta['n_users'], meta['n_items'], meta['k']
+    rel = {c: (torch.from_numpy(z['edges/%s/src' % c[1]]), torch.from_numpy(z['edges/%s/dst' % c[1]])) for c in REL}
+    g = dgl.heterograph(rel, {'user': n_users, 'item': n_items})
+    buys_items = z['edges/buys/dst']
+    pop = np.bincount(buys_items, minlength=n_items).astype(np.float64)
+    pop = (pop / max(pop.sum(), 1.0)).astype(np.float32).reshape(-1, 1)
+    g.nodes['item'].data['popularity'] = torch.from_numpy(pop)
+    g.nodes['user'].data['popularity'] = torch.zeros(n_users, 1)
+    y = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    uids = z['user_ids']
+    with torch.no_grad(), redirect_stdout(io.StringIO()):
+        bought = create_already_bought(g, g.out_edges(u=torch.from_numpy(uids), form='eid', etype='buys'))
+        recs = get_recs(g, y, None, meta['out'], k, uids.tolist(), bought, remove_already_bought=True, cuda=False,
+                        device=None, pred='cos', use_popularity=True, weight_popularity=weight)   # reference code
+    rec_arr = np.full((uids.size, k), -1, dtype=np.int64)
+    for r, u in enumerate(uids.tolist()):
+        rec_arr[r, :len(recs[u])] = np.asarray(recs[u], dtype=np.int64)
+    save_case(base_name + '_pop', dict(base=base_name, weight=weight, k=k), {'popularity': pop, 'recs_pop': rec_arr})
+
+
+def main_popularity():
+    popularity_case('tiny_mean', 1.0, 0)
+    popularity_case('small_mean_128', 0.5, 1)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'popularity':
+    main_popularity()

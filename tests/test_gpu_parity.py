@@ -117,6 +117,44 @@ def test_get_recs_dict_api(grb):
     assert all(list(same[u]) == list(recs[u]) for u in uids)
 
 
+@pytest.mark.parametrize('name', ['tiny_mean', 'small_mean_128'])
+def test_popularity_recs_match_reference(grb, name):
+    """use_popularity=True (src/metrics.py:69-72) against the fixture written by the reference's own get_recs."""
+    meta, z = load_case(name)
+    pmeta, zp = load_case(name + '_pop')
+    g = product_graph(grb, meta, z)
+    g.nodes['item'].data['popularity'] = torch.from_numpy(zp['popularity'])
+    h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    uids = z['user_ids'].tolist()
+    bought = grb.create_already_bought(g, g.out_edges(u=torch.tensor(uids), form='eid', etype='buys'))
+    recs = grb.get_recs(g, h, None, meta['out'], meta['k'], uids, bought, remove_already_bought=True, cuda=True,
+                        device=torch.device('cuda:0'), pred='cos', use_popularity=True, weight_popularity=pmeta['weight'])
+    got = np.stack([np.asarray(recs[u], dtype=np.int64) for u in uids])
+    cos = O.get_recs_scores(h['user'], h['item'], uids).numpy()
+    ratings = np.stack([O.softmax(r) for r in cos]) + zp['popularity'].reshape(1, -1) * pmeta['weight']
+    assert_topk_equivalent(got, zp['recs_pop'], ratings, meta['k'], tol=1e-7)
+
+
+def test_metrics_at_k_match_reference_formula(grb):
+    """recs_to_metrics / get_metrics_at_k (src/metrics.py:81-134) on the device vs the oracle's restatement."""
+    meta, z = load_case('small_mean_128')
+    g = product_graph(grb, meta, z)
+    h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    rng = np.random.default_rng(4)
+    gt_users = rng.integers(0, meta['n_users'], 900)
+    gt_items = rng.integers(0, meta['n_items'], 900)
+    gt_items[:50] = gt_items[50:100]; gt_users[:50] = gt_users[50:100]      # duplicated ground-truth entries
+    bought_eids = torch.arange(g.num_edges('buys'))
+    p, r, c = grb.get_metrics_at_k(h, g, None, meta['out'], (gt_users, gt_items), bought_eids, meta['k'], True, True,
+                                   torch.device('cuda:0'))
+    uids = np.unique(gt_users).tolist()
+    recs = grb.get_recs(g, h, None, meta['out'], meta['k'], uids, grb.create_already_bought(g, bought_eids))
+    truth = grb.create_ground_truth(gt_users, gt_items)
+    wp, wr, wc = O.recs_to_metrics({u: [int(i) for i in v] for u, v in recs.items()}, truth, meta['n_items'])
+    assert (p, r, c) == (wp, wr, wc)
+    assert grb.recs_to_metrics(recs, truth, g) == (wp, wr, wc)
+
+
 def test_forward_scores_and_loss_match_reference(grb):
     meta, z = load_case('fwd_fanout_mean')
     dev = torch.device('cuda:0')

@@ -84,3 +84,26 @@ def test_csr_and_first_appearance():
         assert np.all(np.diff(seg) > 0) and np.all(dst[seg] == v) and np.all(src[seg] == indices[indptr[v]:indptr[v + 1]])
     ids, uniq = O.first_appearance_ids(['b', 'a', 'b', 'c', 'a'])
     assert ids.tolist() == [0, 1, 0, 2, 1] and uniq == ['b', 'a', 'c']
+
+
+@pytest.mark.parametrize('name', ['tiny_mean', 'small_mean_128'])
+def test_popularity_recs_match_reference(name):
+    """use_popularity branch (src/metrics.py:69-72): fixture written by the reference's own get_recs."""
+    meta, z = load_case(name)
+    pmeta, zp = load_case(name + '_pop')
+    hu, hi = torch.from_numpy(z['emb/user']), torch.from_numpy(z['emb/item'])
+    buys = case_relations(z)[('user', 'buys', 'item')]
+    bought = O.create_already_bought(buys[0], buys[1])
+    uids = z['user_ids'].tolist()
+    recs = O.get_recs(hu, hi, meta['k'], uids, bought, popularity=zp['popularity'], weight_popularity=pmeta['weight'])
+    got = np.stack([np.asarray(recs[u], dtype=np.int64) for u in uids])
+    cos = O.get_recs_scores(hu, hi, uids).numpy()
+    ratings = np.stack([O.softmax(r) for r in cos]) + zp['popularity'].reshape(1, -1) * pmeta['weight']
+    assert_topk_equivalent(got, zp['recs_pop'], ratings, meta['k'], tol=1e-7)
+
+
+def test_recs_to_metrics_formula():
+    recs = {0: [1, 2, 3], 1: [4, 5, 6]}
+    truth = {0: [2, 2, 9], 1: [7]}
+    p, r, c = O.recs_to_metrics(recs, truth, 10)
+    assert p == 1 / 6 and r == 2 / 4 and c == 0.6
