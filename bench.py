@@ -189,7 +189,7 @@ def main():
     ap.add_argument('--elem', default='bf16', choices=['bf16', 'fp16'])
     ap.add_argument('--parts', type=int, default=2, choices=[1, 2])
     ap.add_argument('--shortlist', type=int, default=16)
-    ap.add_argument('--item-shards', type=int, default=None, help='N>1: item-range shards (default = world, the north-star layout); 1 = user-range sharding with a replicated item table')
+    ap.add_argument('--item-shards', type=int, default=None, help='N>1 scoring layout: N = item-range shards + owner-side top-k merge; 1 = user-range shards, replicated item table; default: shard the longer side')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true')
     args = ap.parse_args()
@@ -215,6 +215,8 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     n_users, n_items, n_edges, n_layers, agg, hidden, out = wl
+    if args.item_shards is None and world > 1:
+        args.item_shards = D.choose_item_shards(n_users, n_items, world)
     pk = peaks()
 
     # ---- synthetic data (same on every rank: seeded), device CSR, model
@@ -242,6 +244,8 @@ def main():
 
     stage_names = ['embed_in', 'aggregate', 'prep', 'score', 'rescore']
 
+    own_range = [(0, n_users)]  # user range whose recommendations this rank returns
+
     def resident_step(record=None):
         """Inputs resident in HBM. Returns (ids, n_overflow); `record` collects CUDA events per stage."""
         ev = {}
@@ -258,7 +262,7 @@ def main():
         if world == 1:
             h = model.get_repr(blocks, h)
         else:
-            h = D.sharded_get_repr(model, blocks, h)
+            h = D.sharded_get_repr(model, blocks, h, gather_last=('item',) if args.item_shards == 1 else None)
         mark('aggregate')
         if world == 1:
             table = grb.ScoringTable(h['item'], cfg)
@@ -266,7 +270,8 @@ def main():
             ids, scores, n_over = grb.recommend_topk(h['user'], table, K_RECS, bought, return_overflow=True, mark=mark)
         else:
             mark('prep0')
-            ids, scores, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark, item_shards=args.item_shards)
+            ids, scores, owned = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark, item_shards=args.item_shards)
+            own_range[0] = owned
             n_over = torch.zeros(1, dtype=torch.int32, device=dev)
         mark('t1')
         if record is not None:
@@ -284,7 +289,7 @@ def main():
             ids = grb.get_recs_tensor(g, y, K_RECS, uid_all, bought, True, dev, config=cfg)
         else:
             h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
-            h = D.sharded_get_repr(model, blocks, model.embed(h))
+            h = D.sharded_get_repr(model, blocks, model.embed(h), gather_last=('item',) if args.item_shards == 1 else None)
             ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, item_shards=args.item_shards)
         host_ids = ids_pinned[:ids.shape[0]]
         host_ids.copy_(ids, non_blocking=True)
@@ -301,16 +306,22 @@ def main():
         ids, n_over, h = resident_step()
     barrier()
     verified = None
-    if not args.no_verify and world == 1:
-        sample = torch.from_numpy(np.random.default_rng(0).choice(n_users, 512, replace=False)).to(dev)
+    if not args.no_verify:
+        # 512 sampled users of the range this rank owns, against the brute-force fp32 kernel over ALL items
+        ub, ue = own_range[0]
+        sample = torch.from_numpy(ub + np.random.default_rng(rank).choice(ue - ub, min(512, ue - ub), replace=False)).to(dev)
         ex_tab = grb.ScoringTable(h['item'], grb.RecsConfig(exact_only=True))
         ex_ids, ex_sc = grb.recommend_topk(h['user'][sample], ex_tab, K_RECS, bought.select(sample.cpu().numpy()))
         hi_n = torch.nn.functional.normalize(h['item'], dim=1)
         hu_n = torch.nn.functional.normalize(h['user'][sample], dim=1)
-        got = ids[sample].long().clamp(min=0)
-        s_got = (hu_n.unsqueeze(1) * hi_n[got]).sum(-1)
+        mine = ids[sample - ub]
+        s_got = (hu_n.unsqueeze(1) * hi_n[mine.long().clamp(min=0)]).sum(-1)
         s_ex = (hu_n.unsqueeze(1) * hi_n[ex_ids.long().clamp(min=0)]).sum(-1)
-        verified = bool(((s_got - s_ex).abs() < 1e-5).all()) and bool(((ids[sample] < 0) == (ex_ids < 0)).all())
+        verified = bool(((s_got - s_ex).abs() < 1e-5).all()) and bool(((mine < 0) == (ex_ids < 0)).all())
+        if world > 1:
+            t = torch.tensor([1.0 if verified else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            verified = bool(t.item() > 0.5)
 
     # ---- timed: resident inputs, CUDA events, max over ranks
     launches0 = N.kernel_launches()

@@ -76,14 +76,26 @@ def exchange_topk(ids: torch.Tensor, scores: torch.Tensor, group=None) -> Tuple[
     return out_ids.view(world, c, k), out_scores.view(world, c, k), b, e
 
 
-def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
-    """``ConvModel.get_repr`` with destination-range sharding: returns full (all-gathered) tables on every rank."""
+def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None, gather_last=None) -> Dict[str, torch.Tensor]:
+    """``ConvModel.get_repr`` with destination-range sharding. Every layer output is all-gathered (the next layer
+    gathers arbitrary source rows); ``gather_last`` (a collection of node types, default: all) limits the all-gather
+    after the LAST layer -- a table that is not gathered comes back full-height with only this rank's
+    ``shard_range`` rows valid (user-range-sharded scoring needs nothing else of the user table)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     for i, blk in enumerate(blocks):
         ranges = {t: shard_range(blk.number_of_dst_nodes(t), world, rank) for t in blk.dsttypes}
         out = model.layers[i](blk, h, ranges)
-        h = {t: allgather_rows(v, v.shape[0], group) for t, v in out.items()}
+        last = i == len(blocks) - 1
+        h = {t: (allgather_rows(v, v.shape[0], group) if (not last or gather_last is None or t in gather_last) else v)
+             for t, v in out.items()}
     return h
+
+
+def choose_item_shards(n_users: int, n_items: int, world: int) -> int:
+    """Scoring layout: ``world`` = item-range shards + owner-side merge (every rank preps / re-scores ALL users);
+    ``1`` = user-range shards against a replicated item table (every rank preps ALL items, no exchange).
+    The repeated per-row work is what differs, so shard the longer side."""
+    return 1 if n_users >= n_items else world
 
 
 def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought=None, config=None, group=None,
@@ -92,20 +104,26 @@ def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought
     all-gather); ``bought`` rows follow ``h_user`` rows. Returns ``(ids [u_loc, k], scores, (begin, end))`` for the
     user range this rank owns.
 
-    ``item_shards = world`` (default, the layout the north star prescribes): the item table is cut into ``world``
-    contiguous id ranges, every rank scores ALL users against its range and the per-shard exact top-k lists are
-    merged on the rank owning the user range. ``item_shards = 1``: the cross-check layout -- every rank scores only
-    its own user range against the whole (replicated) item table, no exchange; cheaper when users >> items because
-    the per-user prep / re-score work is not repeated on every rank."""
+    ``item_shards = world``: the item table is cut into ``world`` contiguous id ranges, every rank scores ALL
+    users against its range and the per-shard exact top-k lists are merged on the rank owning the user range.
+    ``item_shards = 1``: every rank scores only its own contiguous user range against the whole (replicated) item
+    table -- no exchange, and the per-user prep / re-score work is not repeated on every rank.
+    ``item_shards = None`` (default) picks by ``choose_item_shards`` (shard the longer side)."""
     from . import ops
     from .recs import RecsConfig, ScoringTable, recommend_topk
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     cfg = config or RecsConfig()
-    item_shards = world if item_shards is None else item_shards
+    if item_shards is None:
+        item_shards = choose_item_shards(h_user.shape[0], h_item.shape[0], world)
     if item_shards == 1 and world > 1:
         ub, ue = shard_range(h_user.shape[0], world, rank)
         table = ScoringTable(h_item, cfg)
-        sub = None if bought is None else bought.select(range(ub, ue))
+        sub = None
+        if bought is not None:  # the row slice of this rank, cached on the parent CSR (host slicing + H2D once)
+            cache = bought.__dict__.setdefault('_range_cache', {})
+            if (ub, ue) not in cache:
+                cache[(ub, ue)] = bought.select(range(ub, ue))
+            sub = cache[(ub, ue)]
         ids, scores = recommend_topk(h_user[ub:ue], table, k, sub, mark=mark)
         return ids, scores, (ub, ue)
     if item_shards != world:

@@ -38,7 +38,7 @@ def main():
         buys = data.relations()[('user', 'buys', 'item')]
         bought = grb.BoughtCSR.from_edges(buys[0], buys[1], data.n_users)
         ids1, sc1 = grb.recommend_topk(h1['user'], grb.ScoringTable(h1['item'], grb.RecsConfig()), 10, bought)
-        ids_s, sc_s, (ub, ue) = D.sharded_recommend(hs['user'], hs['item'], 10, bought)
+        ids_s, sc_s, (ub, ue) = D.sharded_recommend(hs['user'], hs['item'], 10, bought, item_shards=world)
         assert ids_s.shape[0] == ue - ub
         hu = torch.nn.functional.normalize(h1['user'][ub:ue], dim=1)
         hi = torch.nn.functional.normalize(h1['item'], dim=1)
@@ -48,6 +48,8 @@ def main():
         assert bool(((ids1[ub:ue] < 0) == (ids_s < 0)).all())
         ids_u, sc_u, (vb, ve) = D.sharded_recommend(hs['user'], hs['item'], 10, bought, item_shards=1)
         assert (vb, ve) == (ub, ue) and torch.equal(ids_u, ids1[ub:ue]), 'user-sharded layout differs (%s)' % agg
+        ids_a, _, _ = D.sharded_recommend(hs['user'], hs['item'], 10, bought)  # default layout (shard the longer side)
+        assert torch.equal(ids_a, ids_u)
         same = float((ids1[ub:ue] == ids_s).float().mean())
         if rank == 0:
             print('multi-gpu check ok: world=%d agg=%s identical ids %.4f (rest are ties < 1e-5)' % (world, agg, same))
