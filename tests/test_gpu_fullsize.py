@@ -1,0 +1,109 @@
+"""Checks at BASELINE.json's bench size (c2: 1M users x 200k items x 50M edges) through size-independent
+properties: the oracle cannot run there in seconds, so rows are sampled and compared against straight torch fp32
+arithmetic on the device, the CSR is compared with a stable device sort, and top-k against the brute-force kernel."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+U, I, E, D = 1_000_000, 200_000, 50_000_000, 128
+
+
+@pytest.fixture(scope='module')
+def world():
+    import gnn_recsys_b200 as grb
+    dev = torch.device('cuda:0')
+    data = grb.make_graph_device(U, I, E, seed=0, device=dev)
+    g = data.graph()
+    blk = g.full_block_on(dev)
+    torch.manual_seed(1)
+    model = grb.ConvModel(g, 2, {'user': 2, 'item': 4, 'hidden': D, 'out': D}).to(dev).eval()
+    with torch.no_grad():
+        h0 = model.embed({t: g.nodes[t].data['features'].to(dev) for t in g.ntypes})
+        h1 = model.get_repr([blk], dict(h0))
+    return dict(grb=grb, dev=dev, data=data, g=g, blk=blk, model=model, h0=h0, h1=h1)
+
+
+def test_csr_is_the_stable_sort_of_the_edge_list(world):
+    grb, dev, g, blk = world['grb'], world['dev'], world['g'], world['blk']
+    for c in (('user', 'clicks', 'item'), ('item', 'bought-by', 'user')):
+        s, d = g.edge_arrays(c)
+        rel = blk.rels[c]
+        dst = torch.from_numpy(d.astype(np.int64)).to(dev)
+        order = torch.sort(dst, stable=True).indices
+        assert torch.equal(rel.eperm.long(), order)
+        assert torch.equal(rel.indices.long(), torch.from_numpy(s.astype(np.int64)).to(dev)[order])
+        counts = torch.bincount(dst, minlength=rel.n_dst)
+        assert torch.equal(rel.indptr[1:].long(), torch.cumsum(counts, 0)) and int(rel.indptr[0]) == 0
+        assert int(rel.indptr[-1]) == rel.nnz == s.shape[0]
+
+
+def test_conv_layer_rows_match_fp32_torch_on_sampled_rows(world):
+    """Layer output of sampled destination rows (incl. the hub items and isolated rows) == relu/norm/sum of plain
+    fp32 torch on the same neighbour lists."""
+    dev, blk, model, h0, h1 = world['dev'], world['blk'], world['model'], world['h0'], world['h1']
+    rng = np.random.default_rng(0)
+    for dt, n in (('item', I), ('user', U)):
+        deg = sum((blk.rels[c].indptr[1:] - blk.rels[c].indptr[:-1]).long() for c in blk.rels if c[2] == dt)
+        rows = np.unique(np.concatenate([rng.choice(n, 300, replace=False), torch.topk(deg, 3).indices.cpu().numpy(),
+                                         torch.nonzero(deg == 0).flatten()[:5].cpu().numpy()]))
+        want = torch.zeros(len(rows), D, device=dev)
+        for c, rel in blk.rels.items():
+            if c[2] != dt:
+                continue
+            layer = model.layers[0].mods[c[1]]
+            ws, wn = layer.fc_self.weight, layer.fc_neigh.weight
+            for j, r in enumerate(rows.tolist()):
+                b, e = int(rel.indptr[r]), int(rel.indptr[r + 1])
+                nb = h0[c[0]][rel.indices[b:e].long()]
+                mean = nb.double().sum(0).float() / max(e - b, 1) if e > b else torch.zeros(D, device=dev)
+                z = torch.relu(h0[dt][r] @ ws.t() + mean @ wn.t())
+                nz = z.norm()
+                want[j] += z / (nz if nz > 0 else 1.0)
+        got = h1[dt][torch.from_numpy(rows).to(dev)]
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+        # every row is a sum of two L2-normalised non-negative vectors
+        nrm = h1[dt].norm(dim=1)
+        assert float(nrm.max()) <= 2.0 + 1e-4 and float(h1[dt].min()) >= 0.0
+
+
+def test_mean_aggregation_is_linear_and_max_is_idempotent(world):
+    grb, dev, blk = world['grb'], world['dev'], world['blk']
+    rel = blk.rels[('user', 'clicks', 'item')]
+    g = torch.Generator(device=dev).manual_seed(3)
+    x, y = torch.rand(U, D, device=dev, generator=g), torch.rand(U, D, device=dev, generator=g)
+    ax = grb.ops.gather_reduce(rel.indptr, rel.indices, None, x, 0)
+    ay = grb.ops.gather_reduce(rel.indptr, rel.indices, None, y, 0)
+    axy = grb.ops.gather_reduce(rel.indptr, rel.indices, None, 2.0 * x + y, 0)
+    torch.testing.assert_close(axy, 2.0 * ax + ay, rtol=1e-4, atol=1e-5)
+    ones = grb.ops.gather_reduce(rel.indptr, rel.indices, None, torch.ones(U, D, device=dev), 0)
+    deg = (rel.indptr[1:] - rel.indptr[:-1])
+    assert torch.equal(ones[:, 0] > 0, deg > 0) and float((ones[deg > 0] - 1).abs().max()) < 1e-5
+    mx = grb.ops.gather_reduce(rel.indptr, rel.indices, None, x, 1)
+    assert bool((mx >= ax - 1e-6).all())                       # max >= mean
+    mx2 = grb.ops.gather_reduce(rel.indptr, rel.indices, None, torch.maximum(x, x), 1)
+    assert torch.equal(mx, mx2)                                 # deterministic, idempotent input transform
+
+
+def test_topk_of_sampled_users_matches_the_brute_force_kernel(world):
+    grb, dev, data, h1 = world['grb'], world['dev'], world['data'], world['h1']
+    buys = data.relations()[('user', 'buys', 'item')]
+    bought = grb.BoughtCSR.from_edges(buys[0], buys[1], U)
+    ids, scores, n_over = grb.recommend_topk(h1['user'], grb.ScoringTable(h1['item'], grb.RecsConfig()), 10, bought,
+                                             return_overflow=True)
+    sample = np.random.default_rng(1).choice(U, 1024, replace=False)
+    st = torch.from_numpy(sample).to(dev)
+    ex_ids, ex_sc = grb.recommend_topk(h1['user'][st], grb.ScoringTable(h1['item'], grb.RecsConfig(exact_only=True)), 10,
+                                       bought.select(sample))
+    hu = torch.nn.functional.normalize(h1['user'][st], dim=1)
+    hi = torch.nn.functional.normalize(h1['item'], dim=1)
+    a = (hu.unsqueeze(1) * hi[ids[st].long()]).sum(-1)
+    b = (hu.unsqueeze(1) * hi[ex_ids.long()]).sum(-1)
+    assert bool(((a - b).abs() < 1e-5).all())
+    assert bool((scores[st, :-1] >= scores[st, 1:]).all())      # sorted
+    srt = torch.sort(ids, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())             # no duplicate recommendation
+    for r in sample[:300].tolist():                             # nothing already bought
+        assert not set(ids[r].tolist()) & set(bought[r])
+    assert int(n_over) < U // 100
