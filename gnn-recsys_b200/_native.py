@@ -40,6 +40,7 @@ SIGNATURES = {
     'gr_colmean_normalized_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     'gr_score_prep': (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     'gr_score_splits': (C.c_int, [_i64, _i64]),
+    'gr_score_pair_mode': (C.c_int, [C.c_int]),
     'gr_score_topk_workspace_bytes': (_sz, [_i64, _i64, _i32]),
     'gr_score_topk_tc': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz,
                                    _vp]),

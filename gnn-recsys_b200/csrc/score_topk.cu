@@ -25,6 +25,8 @@
 //     shortlists are merged by gr_topk_merge (host side of this file).
 #include <cuda.h>
 #include <stdlib.h>
+
+#include <atomic>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -90,6 +92,46 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the even CTA of the cluster is the leader --------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the leader CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -120,9 +162,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D = fp32, A/B = fp16 (0) or bf16 (1), both K-major, N = 128, M = 128.
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format) {
-  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
-         ((uint32_t)(TILE_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format, uint32_t m = TILE_M) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // v[i] for a run-time i over a register array: binary select tree (N - 1 selects), no local memory
@@ -173,33 +214,41 @@ __device__ __noinline__ float shortlist_insert(float s, int gid, int t, int S, f
 
 // Shared-memory plan: [A: UT x PARTS x KB sub-tiles][B ring: `ring` sub-tiles of 16 KB][shortlists][next-bought][barriers]
 constexpr int MAX_RING = 8;
-template <int KB, int PARTS>
+template <int KB, int PARTS, bool PAIR = false>
 struct Cfg {
   static constexpr int A_BYTES = UT * PARTS * KB * SUB_BYTES;
+  static constexpr int SLOT_BYTES = PAIR ? SUB_BYTES / 2 : SUB_BYTES;  // a CTA of a pair holds half of every B sub-tile
   static constexpr int TAIL_BYTES = ROWS_PER_CTA * 4 + 512;  // s_nb + barriers
   static int list_bytes(int S) { return S * ROWS_PER_CTA * 8; }
   static int ring(int S) {
-    const int r = (SMEM_LIMIT - 1024 - A_BYTES - list_bytes(S) - TAIL_BYTES) / SUB_BYTES;
+    const int r = (SMEM_LIMIT - 1024 - A_BYTES - list_bytes(S) - TAIL_BYTES) / SLOT_BYTES;
     return r > MAX_RING ? MAX_RING : r;
   }
-  static size_t smem(int S) { return 1024 /*alignment slack*/ + A_BYTES + (size_t)ring(S) * SUB_BYTES + list_bytes(S) + TAIL_BYTES; }
+  static size_t smem(int S) { return 1024 /*alignment slack*/ + A_BYTES + (size_t)ring(S) * SLOT_BYTES + list_bytes(S) + TAIL_BYTES; }
 };
 
 // MODE (debug / profiling only, see DESIGN.md "pipeline experiments"): 0 = product kernel; 1 = epilogue reads TMEM but
 // skips the top-k scan; 2 = epilogue releases the accumulator without reading it; 3 = MMA warp commits without MMAs.
-template <int KB, int PARTS, int MODE>
+// PAIR: two CTAs of a cluster work as one cta_group::2 unit -- M = 256 MMAs (128 user rows from each CTA), each CTA
+// TMA-loads and holds only HALF of every item sub-tile (64 rows), so the shared-memory and L2 traffic per FLOP halve.
+// The even CTA (leader) issues every MMA; TMA completions of both CTAs land on the leader's barriers, MMA commits
+// are multicast to both CTAs, epilogues of both CTAs release the accumulators on the leader's barriers.
+template <int KB, int PARTS, int MODE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_constant__ CUtensorMap tm_items,
                   long long n_users, long long n_items, long long item_id_base, int tiles_per_split, uint32_t idesc,
                   const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int ring,
                   float* __restrict__ sl_score, int* __restrict__ sl_id) {
-  using L = Cfg<KB, PARTS>;
+  using L = Cfg<KB, PARTS, PAIR>;
   constexpr int D_PAD = KB * KBLK;
+  constexpr int SLOT = L::SLOT_BYTES;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
   uint8_t* sB = sA + L::A_BYTES;
-  float* ls = reinterpret_cast<float*>(sB + ring * SUB_BYTES);  // [S][256]
+  float* ls = reinterpret_cast<float*>(sB + ring * SLOT);  // [S][256]
   int* li = reinterpret_cast<int*>(ls + S * ROWS_PER_CTA);       // [S][256]
   int* s_nb = li + S * ROWS_PER_CTA;                              // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_nb + ROWS_PER_CTA);
@@ -219,35 +268,49 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < ring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(a_full, 1);
-    for (int i = 0; i < UT * 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < UT * 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation: all 512 columns (this kernel runs one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================= TMA producer: one 16 KB sub-tile (64 K-elements of one part of one item tile) per ring slot
     if (lane == 0 && n_tiles > 0) {
-      mbar_expect_tx(a_full, L::A_BYTES);
+      if (leader) mbar_expect_tx(a_full, (PAIR ? 2 : 1) * L::A_BYTES);
       for (int ut = 0; ut < UT; ++ut)
         for (int pa = 0; pa < PARTS; ++pa)
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_2d(sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES, &tm_users, pa * D_PAD + kb * KBLK,
-                        (int)(row_base + ut * TILE_M), a_full);
+          for (int kb = 0; kb < KB; ++kb) {
+            void* dst = sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES;
+            if (PAIR) tma_load_2d_pair(dst, &tm_users, pa * D_PAD + kb * KBLK, (int)(row_base + ut * TILE_M), a_full);
+            else tma_load_2d(dst, &tm_users, pa * D_PAD + kb * KBLK, (int)(row_base + ut * TILE_M), a_full);
+          }
       int buf = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         for (int pb = 0; pb < PARTS; ++pb) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(empty + buf, phase ^ 1u);
-            mbar_expect_tx(full + buf, SUB_BYTES);
-            tma_load_2d(sB + buf * SUB_BYTES, &tm_items, pb * D_PAD + kb * KBLK, (tile0 + j) * TILE_N, full + buf);
+            if (PAIR) {  // this CTA's 64 rows of the 128-item sub-tile; the bytes of both halves count on the leader
+              if (leader) mbar_expect_tx(full + buf, SUB_BYTES);
+              tma_load_2d_pair(sB + buf * SLOT, &tm_items, pb * D_PAD + kb * KBLK,
+                               (tile0 + j) * TILE_N + (int)crank * (TILE_N / 2), full + buf);
+            } else {
+              mbar_expect_tx(full + buf, SUB_BYTES);
+              tma_load_2d(sB + buf * SLOT, &tm_items, pb * D_PAD + kb * KBLK, (tile0 + j) * TILE_N, full + buf);
+            }
             if (++buf == ring) { buf = 0; phase ^= 1u; }
           }
         }
@@ -255,7 +318,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0 && n_tiles > 0) {
+    if (lane == 0 && n_tiles > 0 && leader) {
       mbar_wait(a_full, 0);
       tc_fence_after();
       int buf = 0;
@@ -268,7 +331,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(full + buf, phase);
             tc_fence_after();
-            const uint64_t db = make_desc_sw128(smem_u32(sB + buf * SUB_BYTES));
+            const uint64_t db = make_desc_sw128(smem_u32(sB + buf * SLOT));
             for (int ut = 0; ut < UT; ++ut) {
               const uint32_t d_tmem = tmem_base + (uint32_t)((ut * 2 + slot) * TILE_N);
               if (pb == 0 && kb == 0) {  // accumulator slot must have been drained by the epilogue of tile j - 2
@@ -281,13 +344,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
                 const uint64_t da = make_desc_sw128(smem_u32(sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES));
 #pragma unroll
                 for (int k = 0; k < KBLK / UMMA_K; ++k)  // +32 bytes (>>4 = 2) per K = 16 step inside the swizzle atom
-                  if (MODE != 3)
-                    tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                               (pb | kb | pa | k) != 0 ? 1u : 0u);
+                  if (MODE != 3) {
+                    if (PAIR) tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                              (pb | kb | pa | k) != 0 ? 1u : 0u);
+                    else tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                    (pb | kb | pa | k) != 0 ? 1u : 0u);
+                  }
               }
-              if (pb == PARTS - 1 && kb == KB - 1) tc_commit(t_full + ut * 2 + slot);
+              if (pb == PARTS - 1 && kb == KB - 1) {
+                if (PAIR) tc_commit_pair(t_full + ut * 2 + slot); else tc_commit(t_full + ut * 2 + slot);
+              }
             }
-            tc_commit(empty + buf);
+            if (PAIR) tc_commit_pair(empty + buf); else tc_commit(empty + buf);
             if (++buf == ring) { buf = 0; phase ^= 1u; }
           }
         }
@@ -333,7 +401,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + ut * 2 + slot);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(t_empty + ut * 2 + slot); else mbar_arrive(t_empty + ut * 2 + slot);
+      }
       if (MODE == 2) continue;
       if (MODE == 1) {
         if (__uint_as_float(v[lane]) == 123456.f) tau = 0.f;  // keep the loads alive
@@ -375,9 +445,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still be reading its half of the accumulators / our barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -401,12 +473,12 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // [rows][row_elems] 16-bit row-major -> 2-D tensor map with a {64 elements, 128 rows} box, 128-byte swizzle, zero OOB fill
-int make_map(CUtensorMap* map, const uint16_t* ptr, long long rows, int row_elems, int elem_type) {
+int make_map(CUtensorMap* map, const uint16_t* ptr, long long rows, int row_elems, int elem_type, int box_rows = TILE_M) {
   auto enc = get_encode_fn();
   GR_REQUIRE(enc != nullptr, GR_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)row_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)TILE_M};
+  cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, elem_type == GR_ELEM_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                    2, const_cast<uint16_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -416,10 +488,10 @@ int make_map(CUtensorMap* map, const uint16_t* ptr, long long rows, int row_elem
 }
 
 struct ScoreArgs {
-  CUtensorMap mu, mi;
+  CUtensorMap mu, mi, mi_half;  // mi_half: 64-row boxes, the half sub-tile a CTA of a pair loads
   long long n_users, n_items, item_id_base;
   int splits, tiles_per_split;
-  uint32_t idesc;
+  uint32_t ab_format;
   const long long* bptr;
   const int* bids;
   int S;
@@ -427,17 +499,35 @@ struct ScoreArgs {
   int* sl_id;
 };
 
-template <int KB, int PARTS, int MODE = 0>
+template <int KB, int PARTS, int MODE = 0, bool PAIR = false>
 int launch_score(const ScoreArgs& a, cudaStream_t st) {
-  auto kern = score_topk_kernel<KB, PARTS, MODE>;
-  using L = Cfg<KB, PARTS>;
+  auto kern = score_topk_kernel<KB, PARTS, MODE, PAIR>;
+  using L = Cfg<KB, PARTS, PAIR>;
   const int ring = L::ring(a.S);
   GR_REQUIRE(ring >= 2, GR_E_INVALID, "shortlist too large for the shared-memory budget of this configuration");
   const size_t smem = L::smem(a.S);
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((a.n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA), (unsigned)a.splits);
-  kern<<<grid, NUM_THREADS, smem, st>>>(a.mu, a.mi, a.n_users, a.n_items, a.item_id_base, a.tiles_per_split, a.idesc,
-                                        a.bptr, a.bids, a.S, ring, a.sl_score, a.sl_id);
+  unsigned gx = (unsigned)((a.n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+  const uint32_t idesc = PAIR ? make_idesc(a.ab_format, 2 * TILE_M) : make_idesc(a.ab_format);
+  if (PAIR) {
+    gx = (gx + 1) & ~1u;  // whole CTA pairs; the rows of a surplus CTA are out of range (TMA zero fill, not stored)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, (unsigned)a.splits);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GR_CUDA(cudaLaunchKernelEx(&cfg, kern, a.mu, a.mi_half, a.n_users, a.n_items, a.item_id_base, a.tiles_per_split,
+                               idesc, a.bptr, a.bids, a.S, ring, a.sl_score, a.sl_id));
+  } else {
+    kern<<<dim3(gx, (unsigned)a.splits), NUM_THREADS, smem, st>>>(a.mu, a.mi, a.n_users, a.n_items, a.item_id_base,
+                                                                  a.tiles_per_split, idesc, a.bptr, a.bids, a.S, ring,
+                                                                  a.sl_score, a.sl_id);
+  }
   GR_LAUNCH_CHECK();
   return GR_OK;
 }
@@ -453,7 +543,15 @@ int choose_splits(long long n_users, long long n_items) {
   return (int)std::max<long long>(s, 1);
 }
 
+// 1 = CTA-pair kernel (default), 0 = single-CTA kernel; GR_SCORE_PAIR in the environment sets the initial value
+std::atomic<int> g_pair_mode{getenv("GR_SCORE_PAIR") ? atoi(getenv("GR_SCORE_PAIR")) : 1};
+
 }  // namespace
+
+extern "C" int gr_score_pair_mode(int set_or_negative) {
+  if (set_or_negative >= 0) g_pair_mode.store(set_or_negative != 0 ? 1 : 0);
+  return g_pair_mode.load();
+}
 
 extern "C" int gr_score_splits(int64_t n_users, int64_t n_items) {
   if (n_users <= 0 || n_items <= 0) return 1;
@@ -498,11 +596,13 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   if (rc != GR_OK) return rc;
   rc = make_map(&a.mi, items_q, n_items, d_pad * parts, elem_type);
   if (rc != GR_OK) return rc;
+  rc = make_map(&a.mi_half, items_q, n_items, d_pad * parts, elem_type, TILE_N / 2);
+  if (rc != GR_OK) return rc;
   a.n_users = n_users; a.n_items = n_items; a.item_id_base = item_id_base;
   a.splits = choose_splits(n_users, n_items);
   const int tiles = (int)((n_items + TILE_N - 1) / TILE_N);
   a.tiles_per_split = (tiles + a.splits - 1) / a.splits;
-  a.idesc = make_idesc(elem_type == GR_ELEM_FP16 ? 0u : 1u);
+  a.ab_format = elem_type == GR_ELEM_FP16 ? 0u : 1u;
   a.bptr = reinterpret_cast<const long long*>(bought_indptr_or_null);
   a.bids = bought_ids_or_null;
   a.S = shortlist;
@@ -516,6 +616,9 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   }
   a.sl_score = part_score; a.sl_id = part_id;
   static const int debug_mode = getenv("GR_SCORE_DEBUG_MODE") ? atoi(getenv("GR_SCORE_DEBUG_MODE")) : 0;
+  if (g_pair_mode.load() != 0 && debug_mode == 0 && d_pad == 128) {  // CTA-pair (cta_group::2) kernel: the default
+    rc = parts == 1 ? launch_score<2, 1, 0, true>(a, st) : launch_score<2, 2, 0, true>(a, st);
+  } else
   if (debug_mode != 0 && d_pad == 128 && parts == 2) {  // pipeline experiments (results are NOT valid top-k lists)
     rc = debug_mode == 1 ? launch_score<2, 2, 1>(a, st) : debug_mode == 2 ? launch_score<2, 2, 2>(a, st) : launch_score<2, 2, 3>(a, st);
   } else if (debug_mode != 0 && d_pad == 128 && parts == 1) {

@@ -120,6 +120,9 @@ int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, float* cente
 int gr_score_prep(const float* x, int64_t n, int32_t d, const float* center_or_null, int32_t d_pad, int32_t parts,
                   int32_t elem_type, uint16_t* out_q, float* stats_or_null, gr_stream_t stream);
 int gr_score_splits(int64_t n_users, int64_t n_items);
+/* stage-1 kernel variant: 1 = CTA pairs (tcgen05 cta_group::2, M = 256, each CTA holds half of every item tile;
+ * default), 0 = single CTA (cta_group::1). Pass a negative value to query. Same results, ~5 % apart under power cap. */
+int gr_score_pair_mode(int set_or_negative);
 size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t shortlist);
 int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const uint16_t* items_q, int64_t n_items,
                      int64_t item_id_base, int32_t d_pad, int32_t parts, int32_t elem_type,

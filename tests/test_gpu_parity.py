@@ -371,9 +371,20 @@ def test_quantised_scores_within_error_bound(grb, cfg):
     assert float((top[:, -1] - got.min(1).values).max()) <= 2 * bound
 
 
+@pytest.mark.parametrize('pair', [1, 0], ids=['cta_pair', 'single_cta'])
 @pytest.mark.parametrize('shape', [(1000, 20000), (70000, 3000), (257, 129), (5, 40)])
-def test_recs_large_vs_exact_kernel_and_oracle(grb, shape):
-    """Tensor-core path == brute-force fp32 kernel == oracle (vectorised) on clustered embeddings with bought lists."""
+def test_recs_large_vs_exact_kernel_and_oracle(grb, shape, pair):
+    """Tensor-core path (both kernel variants) == brute-force fp32 kernel == oracle (vectorised) on clustered
+    embeddings with bought lists."""
+    lib = grb._native.load()
+    lib.gr_score_pair_mode(pair)
+    try:
+        _recs_large(grb, shape)
+    finally:
+        lib.gr_score_pair_mode(1)
+
+
+def _recs_large(grb, shape):
     n_u, n_i = shape
     rng = np.random.default_rng(n_u)
     d, k = 128, 10
