@@ -41,7 +41,8 @@ constexpr int UMMA_K = 16;
 constexpr int SUB_BYTES = TILE_M * KBLK * 2;  // one [128 rows][64 x 16 bit] swizzled sub-tile = 16 KB
 constexpr int ROWS_PER_CTA = TILE_M * UT;     // 256
 constexpr int EPI_WARPS = 4 * UT;
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // 320
+constexpr int MMA_WARP1 = 2 + EPI_WARPS;              // second MMA issuer (user tile 1); warp 1 issues user tile 0
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32;  // 352
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
 
@@ -266,7 +267,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   const long long row_base = (long long)blockIdx.x * ROWS_PER_CTA;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < ring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < ring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, UT); }  // one commit per issuer
     mbar_init(a_full, 1);
     for (int i = 0; i < UT * 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -316,8 +317,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 || warp == MMA_WARP1) {
+    // ================= MMA issuers: one thread per user tile (a single thread cannot issue 48 MMAs per item tile
+    // fast enough to keep the tensor pipe busy: ~13 SASS instructions of descriptor traffic per MMA) =================
+    const int ut = warp == 1 ? 0 : 1;
     if (lane == 0 && n_tiles > 0 && leader) {
       mbar_wait(a_full, 0);
       tc_fence_after();
@@ -332,7 +335,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
             mbar_wait(full + buf, phase);
             tc_fence_after();
             const uint64_t db = make_desc_sw128(smem_u32(sB + buf * SLOT));
-            for (int ut = 0; ut < UT; ++ut) {
+            {
               const uint32_t d_tmem = tmem_base + (uint32_t)((ut * 2 + slot) * TILE_N);
               if (pb == 0 && kb == 0) {  // accumulator slot must have been drained by the epilogue of tile j - 2
                 mbar_wait(t_empty + ut * 2 + slot, aphase ^ 1u);
@@ -361,7 +364,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
         }
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     // ================= epilogue: one thread = one user row =================
     const int ew = warp - 2;
     const int ut = ew >> 2;
