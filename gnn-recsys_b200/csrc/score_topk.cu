@@ -535,21 +535,26 @@ int launch_score(const ScoreArgs& a, cudaStream_t st) {
   return GR_OK;
 }
 
-// item-range splits: enough CTAs for two waves when the user count alone cannot fill the chip
+// item-range splits: enough CTAs for two waves when the user count alone cannot fill the chip. (Splitting further
+// to shorten a nearly empty last wave was measured and rejected: every split restarts its shortlists, and the
+// warm-up insertions cost more than the wave round-up saves -- 250k x 200k: 29.6 ms unsplit, 39.5 ms in 3 splits.)
 int choose_splits(long long n_users, long long n_items) {
-  const long long ctas = (n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  static const int forced = getenv("GR_SCORE_SPLITS") ? atoi(getenv("GR_SCORE_SPLITS")) : 0;  // experiments only
+  if (forced > 0) return (int)std::min<long long>(forced, std::max<long long>(1, (n_items + TILE_N - 1) / TILE_N));
+  long long ctas = (n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+  ctas += ctas & 1;  // CTA pairs
   const long long tiles = (n_items + TILE_N - 1) / TILE_N;
   const long long want = 2LL * gr::sm_count();
   if (ctas >= want || tiles <= 1) return 1;
-  long long s = (want + ctas - 1) / ctas;
-  s = std::min<long long>(s, std::min<long long>(tiles, GR_SCORE_MAX_SPLITS));
-  return (int)std::max<long long>(s, 1);
+  long long sp = (want + ctas - 1) / ctas;
+  sp = std::min<long long>(sp, std::min<long long>(tiles, GR_SCORE_MAX_SPLITS));
+  return (int)std::max<long long>(sp, 1);
 }
 
-// 1 = CTA-pair kernel (default), 0 = single-CTA kernel; GR_SCORE_PAIR in the environment sets the initial value
-std::atomic<int> g_pair_mode{getenv("GR_SCORE_PAIR") ? atoi(getenv("GR_SCORE_PAIR")) : 1};
-
 }  // namespace
+
+// 1 = CTA-pair kernel (default), 0 = single-CTA kernel; GR_SCORE_PAIR in the environment sets the initial value
+static std::atomic<int> g_pair_mode{getenv("GR_SCORE_PAIR") ? atoi(getenv("GR_SCORE_PAIR")) : 1};
 
 extern "C" int gr_score_pair_mode(int set_or_negative) {
   if (set_or_negative >= 0) g_pair_mode.store(set_or_negative != 0 ? 1 : 0);
