@@ -32,6 +32,7 @@ SIGNATURES = {
     'gr_linear_workspace_bytes': (_sz, [_i32, _i32]),
     'gr_linear_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, C.c_int, _vp, _vp, _sz, _vp]),
     'gr_sage_relation_workspace_bytes': (_sz, [_i64, _i32]),
+    'gr_sage_epilogue_mode': (C.c_int, [C.c_int]),
     'gr_sage_relation_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _i32, C.c_int,
                                        C.c_int, C.c_int, _f32, _vp, _vp, _sz, _vp]),
     'gr_gather_reduce_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, C.c_int, _vp, _vp, _sz, _vp]),

@@ -16,7 +16,10 @@
 //
 // Sum order: neighbours are accumulated in CSR (edge-id) order like the sequential CPU loop of the oracle; mean
 // divides by the degree (IEEE division) exactly like `sum / clamp(deg, 1)`.
+#include <cuda_fp16.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "common.cuh"
@@ -140,6 +143,40 @@ __device__ __forceinline__ int find_long(const int* __restrict__ long_rows, int 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(FULL, found, o));
   return found;
+}
+
+// Reduced neighbour row of `row` in registers: lane l holds columns 4 * (l + 32 q) .. + 3 in acc[q].
+template <int VN, bool MAXR>
+__device__ __forceinline__ void reduce_row_regs(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                const float* __restrict__ ew, const float* __restrict__ h, int d,
+                                                int row, int lane, const LongWs& lw, float4 (&acc)[VN]) {
+  const int beg = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+  const int deg = end - beg;
+  if (deg > LONG_ROW) {
+    const int idx = find_long(lw.long_rows, lw.counters[0], row, lane);
+#pragma unroll
+    for (int q = 0; q < VN; ++q) {
+      const int c = (lane + 32 * q) * 4;
+      acc[q] = c < d ? *reinterpret_cast<const float4*>(lw.long_agg + (size_t)idx * d + c) : make_float4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < VN; ++q) acc[q] = ident4<MAXR>();
+    gather_range<VN, MAXR>(indices, ew, h, d, beg, end, lane, acc);
+#pragma unroll
+    for (int q = 0; q < VN; ++q) acc[q] = finalize4<MAXR>(acc[q], deg);
+  }
+}
+__device__ __forceinline__ float absmax4(const float4& v) {
+  return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+__device__ __forceinline__ float4 scale4(const float4& v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
+// power of two that brings m into [1, 2) (1 for m == 0 or non-finite): multiplying by it is exact
+__device__ __forceinline__ float pow2_scale(float m) {
+  int e = (__float_as_int(m) >> 23) & 0xff;
+  if (e == 0 || e == 0xff) return 1.f;
+  e = max(min(254 - e, 200), 54);
+  return __int_as_float(e << 23);
 }
 
 // Reduced neighbour row of `row` -> dst (shared or global, 16-byte aligned rows of d floats).
@@ -292,6 +329,64 @@ __global__ void pack_weights_kernel(const float* __restrict__ ws_t, const float*
   }
 }
 
+// ---- fp16 split variant (default): the same hi/lo idea on mma.sync.m16n8k16.f16 -- half the MMA instructions of the
+// tf32 path at twice the rate. fp16 has 11 significant bits like tf32 but only 5 exponent bits, so every tile row is
+// scaled by a power of two that brings its largest |value| (self and neighbour part together) into [1, 2), and the
+// weights by one global power of two; both are exact, cancel in the L2 normalisation and are divided out otherwise.
+// Error: <= 2^-25 absolute per scaled element (lo halves go subnormal), ~0.5 % of the rtol 1e-4 / atol 1e-5 budget,
+// independent of the input scale (build/exp_split2.py).
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// wscale[0] = power of two bringing max |W| into [1, 2), wscale[1] = its inverse
+__global__ void __launch_bounds__(1024) weight_scale_kernel(const float* __restrict__ ws_t, const float* __restrict__ wn_t,
+                                                            int n_self, int n_neigh, float* __restrict__ wscale) {
+  __shared__ float s_red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n_self; i += blockDim.x) m = fmaxf(m, fabsf(ws_t[i]));
+  for (int i = threadIdx.x; i < n_neigh; i += blockDim.x) m = fmaxf(m, fabsf(wn_t[i]));
+  m = gr::warp_max(m);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = gr::warp_max(threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f);
+    if (threadIdx.x == 0) {
+      const float sc = pow2_scale(m);
+      wscale[0] = sc;
+      wscale[1] = 1.f / sc;
+    }
+  }
+}
+
+// packed[(ks * n_tiles + nt) * 32 + lane] = {b0_hi, b1_hi, b0_lo, b1_lo} (each two fp16) of the m16n8k16 B fragment:
+// b0 = W[ks*16 + 2*(lane%4) + {0,1}][nt*8 + lane/4], b1 = the same rows + 8; W = wscale * [W_self^T ; W_neigh^T].
+__global__ void pack_weights_f16_kernel(const float* __restrict__ ws_t, const float* __restrict__ wn_t, int ds, int dn,
+                                        int dout, const float* __restrict__ wscale, uint4* __restrict__ packed) {
+  const int n_tiles = dout / 8, k_steps = (ds + dn) / 16;
+  const int total = k_steps * n_tiles * 32;
+  const float sc = wscale[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, nt = (i >> 5) % n_tiles, ks = (i >> 5) / n_tiles;
+    const int k0 = ks * 16 + 2 * (lane & 3), n = nt * 8 + (lane >> 2);
+    auto w = [&](int k) { return sc * (k < ds ? ws_t[(size_t)k * dout + n] : wn_t[(size_t)(k - ds) * dout + n]); };
+    uint4 o;
+    split_f16x2(w(k0), w(k0 + 1), o.x, o.z);
+    split_f16x2(w(k0 + 8), w(k0 + 9), o.y, o.w);
+    packed[i] = o;
+  }
+}
+
 struct SageParams {
   const int* indptr; const int* indices; const float* ew;
   const float* h_src; const float* h_dst;
@@ -302,21 +397,24 @@ struct SageParams {
   float z_scale;
   float* out;
   const float4* packed;  // pre-split weights in B-fragment order (fused kernel only)
+  const float* wscale;   // fp16 variant: {2^p, 2^-p} applied to the weights
 };
 
-constexpr int PAD = 4;  // floats of row padding in the shared-memory tiles
+constexpr int PAD_TF32 = 4, PAD_F16 = 8;  // floats of row padding: conflict-free 32-bit / 64-bit fragment loads
 
 // MT = 16-row m-tiles per warp (tile rows R = 32 * MT: two row groups), NT = 8-column n-tiles per warp
 // (d_out = 32 * NT: four column groups). VN / VS = float4 per lane of a neighbour / self row.
-template <int VN, int VS, int NT, int MT, bool MAXR>
+template <int VN, int VS, int NT, int MT, bool MAXR, bool F16>
 __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fused_kernel(SageParams p, LongWs lw) {
   constexpr int R = 32 * MT;
+  constexpr int PAD = F16 ? PAD_F16 : PAD_TF32;
   extern __shared__ __align__(16) float smem[];
   const int pn = p.dn + PAD, ps = p.ds + PAD;
   float* sN = smem;            // [R][dn + PAD]
   float* sS = smem + R * pn;   // [R][ds + PAD]
   __shared__ int s_next;
   __shared__ float s_part[4][R];
+  __shared__ float s_inv[R];  // F16: 1 / row scale
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = p.row_begin + (int64_t)blockIdx.x * R;
   if (threadIdx.x == 0) s_next = 0;
@@ -330,13 +428,35 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
     if (r >= R) break;
     const int64_t row = row0 + r;
     if (row < p.row_end) {
-      reduce_row_to<VN, MAXR>(p.indptr, p.indices, p.ew, p.h_src, p.dn, (int)row, lane, lw, sN + r * pn);
+      float4 an[VN], as[VS];
+      reduce_row_regs<VN, MAXR>(p.indptr, p.indices, p.ew, p.h_src, p.dn, (int)row, lane, lw, an);
 #pragma unroll
       for (int q = 0; q < VS; ++q) {
         const int c = (lane + 32 * q) * 4;
-        if (c < p.ds) *reinterpret_cast<float4*>(sS + r * ps + c) = gr::ldg_f4(p.h_dst + (size_t)row * p.ds + c);
+        as[q] = c < p.ds ? gr::ldg_f4(p.h_dst + (size_t)row * p.ds + c) : make_float4(0, 0, 0, 0);
+      }
+      float sc = 1.f;
+      if (F16) {  // one exact power-of-two scale per row, shared by its self and neighbour part
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < VN; ++q) m = fmaxf(m, absmax4(an[q]));
+#pragma unroll
+        for (int q = 0; q < VS; ++q) m = fmaxf(m, absmax4(as[q]));
+        sc = pow2_scale(gr::warp_max(m));
+        if (lane == 0) s_inv[r] = 1.f / sc;
+      }
+#pragma unroll
+      for (int q = 0; q < VN; ++q) {
+        const int c = (lane + 32 * q) * 4;
+        if (c < p.dn) *reinterpret_cast<float4*>(sN + r * pn + c) = F16 ? scale4(an[q], sc) : an[q];
+      }
+#pragma unroll
+      for (int q = 0; q < VS; ++q) {
+        const int c = (lane + 32 * q) * 4;
+        if (c < p.ds) *reinterpret_cast<float4*>(sS + r * ps + c) = F16 ? scale4(as[q], sc) : as[q];
       }
     } else {
+      if (F16 && lane == 0) s_inv[r] = 1.f;
       for (int c = lane * 4; c < p.dn; c += 128) *reinterpret_cast<float4*>(sN + r * pn + c) = make_float4(0, 0, 0, 0);
       for (int c = lane * 4; c < p.ds; c += 128) *reinterpret_cast<float4*>(sS + r * ps + c) = make_float4(0, 0, 0, 0);
     }
@@ -359,6 +479,41 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
   float4 bq[NT];
 #pragma unroll
   for (int n = 0; n < NT; ++n) bq[n] = __ldg(wp + (size_t)n * 32);
+  if (F16) {
+    const int ks16_self = p.ds / 16, ks16_all = (p.ds + p.dn) / 16;
+    for (int ks = 0; ks < ks16_all; ++ks) {
+      float4 bcur[NT];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) bcur[n] = bq[n];
+      if (ks + 1 < ks16_all) {
+        const float4* nx = wp + (size_t)(ks + 1) * n_tiles * 32;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) bq[n] = __ldg(nx + (size_t)n * 32);
+      }
+      const float* tile = ks < ks16_self ? sS : sN;
+      const int pitch = ks < ks16_self ? ps : pn;
+      const int kc = (ks < ks16_self ? ks : ks - ks16_self) * 16 + 2 * tig;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float* a = tile + (rg * (R / 2) + m * 16 + g) * pitch + kc;
+        const float2 x0 = *reinterpret_cast<const float2*>(a), x1 = *reinterpret_cast<const float2*>(a + 8 * pitch);
+        const float2 x2 = *reinterpret_cast<const float2*>(a + 8), x3 = *reinterpret_cast<const float2*>(a + 8 * pitch + 8);
+        uint32_t ah[4], al[4];
+        split_f16x2(x0.x, x0.y, ah[0], al[0]);
+        split_f16x2(x1.x, x1.y, ah[1], al[1]);
+        split_f16x2(x2.x, x2.y, ah[2], al[2]);
+        split_f16x2(x3.x, x3.y, ah[3], al[3]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const uint32_t bh0 = __float_as_uint(bcur[n].x), bh1 = __float_as_uint(bcur[n].y);
+          const uint32_t bl0 = __float_as_uint(bcur[n].z), bl1 = __float_as_uint(bcur[n].w);
+          mma_f16(acc[m][n], al, bh0, bh1);
+          mma_f16(acc[m][n], ah, bl0, bl1);
+          mma_f16(acc[m][n], ah, bh0, bh1);
+        }
+      }
+    }
+  } else
   for (int ks = 0; ks < ks_all; ++ks) {
     float4 bcur[NT];
 #pragma unroll
@@ -427,12 +582,15 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
         nrm = sqrtf((s_part[0][r] + s_part[1][r]) + (s_part[2][r] + s_part[3][r]));
         if (nrm == 0.f) nrm = 1.f;
       }
+      float unscale = 1.f;
+      if (F16 && !p.l2norm) unscale = s_inv[r] * __ldg(p.wscale + 1);  // exact powers of two
       if (row < p.row_end) {
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
           float* o = p.out + (size_t)row * p.dout + cg * (NT * 8) + n * 8 + 2 * tig;
           float z0 = acc[m][n][2 * h], z1 = acc[m][n][2 * h + 1];
           if (p.l2norm) { z0 = z0 / nrm; z1 = z1 / nrm; }
+          else if (F16) { z0 *= unscale; z1 *= unscale; }
           if (p.accumulate == GR_ACC_ADD) {
             const float2 prev = *reinterpret_cast<const float2*>(o);
             z0 = prev.x + z0; z1 = prev.y + z1;
@@ -549,11 +707,11 @@ int launch_long_rows(const int* indptr, const int* indices, const float* ew, con
   return GR_OK;
 }
 
-template <int VN, int VS, int NT, int MT, bool MAXR>
+template <int VN, int VS, int NT, int MT, bool MAXR, bool F16>
 int launch_fused(const SageParams& p, const LongWs& lw, cudaStream_t st) {
   constexpr int R = 32 * MT;
-  const size_t smem = sizeof(float) * R * (p.dn + p.ds + 2 * PAD);
-  auto kern = sage_fused_kernel<VN, VS, NT, MT, MAXR>;
+  const size_t smem = sizeof(float) * R * (p.dn + p.ds + 2 * (F16 ? PAD_F16 : PAD_TF32));
+  auto kern = sage_fused_kernel<VN, VS, NT, MT, MAXR, F16>;
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int64_t rows = p.row_end - p.row_begin;
@@ -563,12 +721,12 @@ int launch_fused(const SageParams& p, const LongWs& lw, cudaStream_t st) {
   return GR_OK;
 }
 
-template <bool MAXR>
+template <bool MAXR, bool F16>
 int dispatch_fused(const SageParams& p, const LongWs& lw, cudaStream_t st, bool* handled) {
   *handled = true;
   const int vn = (p.dn + 127) / 128, vs = (p.ds + 127) / 128;
 #define GR_CASE(VN_, VS_, NT_, MT_) \
-  if (vn == VN_ && vs == VS_ && p.dout == 32 * NT_) return launch_fused<VN_, VS_, NT_, MT_, MAXR>(p, lw, st);
+  if (vn == VN_ && vs == VS_ && p.dout == 32 * NT_) return launch_fused<VN_, VS_, NT_, MT_, MAXR, F16>(p, lw, st);
   GR_CASE(1, 1, 4, 2)  // 128 -> 128 (c1, c2, c5): 64-row tiles
   GR_CASE(1, 1, 2, 2)  // .. -> 64
   GR_CASE(2, 2, 8, 1)  // 256 -> 256 (c3 hidden): 32-row tiles
@@ -585,9 +743,17 @@ bool fast_dims(int dn, int ds, int dout) {
          (dout == 64 || dout == 128 || dout == 256);
 }
 
-size_t packed_bytes(int dn, int ds, int dout) { return gr::align_up((size_t)(dn + ds) * dout * 2 * sizeof(float), 256); }
+size_t packed_bytes(int dn, int ds, int dout) { return gr::align_up((size_t)(dn + ds) * dout * 2 * sizeof(float), 256) + 256; }
+
+// projection epilogue: 1 = fp16 split on m16n8k16 (default), 0 = tf32 split on m16n8k8
+std::atomic<int> g_epilogue_f16{1};
 
 }  // namespace
+
+extern "C" int gr_sage_epilogue_mode(int set_or_negative) {
+  if (set_or_negative >= 0) g_epilogue_f16.store(set_or_negative != 0 ? 1 : 0);
+  return g_epilogue_f16.load();
+}
 
 extern "C" size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh) {
   return long_ws_layout(nnz < 0 ? 0 : nnz, d_neigh, nullptr, nullptr) + packed_bytes(256, 256, 256);
@@ -608,7 +774,7 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
   GR_REQUIRE(nnz == 0 || indices, GR_E_INVALID, "null indices");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SageParams p{indptr, indices, edge_w_or_null, h_src, h_dst, row_begin, row_end, d_neigh, d_self, d_out,
-               w_self_t, w_neigh_t, l2norm, accumulate, z_scale, out, nullptr};
+               w_self_t, w_neigh_t, l2norm, accumulate, z_scale, out, nullptr, nullptr};
   const bool maxr = reducer == GR_REDUCE_MAX;
   LongWs lw{};
   if (fast_dims(d_neigh, d_self, d_out)) {
@@ -617,13 +783,23 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
     GR_REQUIRE(ws != nullptr && ws_bytes >= need, GR_E_WORKSPACE, "workspace too small");
     GR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, GR_E_INVALID, "workspace must be 256-byte aligned");
     long_ws_layout(nnz, d_neigh, &lw, static_cast<char*>(ws));
-    float4* packed = reinterpret_cast<float4*>(static_cast<char*>(ws) + long_bytes);
-    {
+    float* wscale = reinterpret_cast<float*>(static_cast<char*>(ws) + long_bytes);
+    float4* packed = reinterpret_cast<float4*>(static_cast<char*>(ws) + long_bytes + 256);
+    const bool f16 = g_epilogue_f16.load() != 0 && d_neigh % 16 == 0 && d_self % 16 == 0;
+    if (f16) {
+      weight_scale_kernel<<<1, 1024, 0, st>>>(w_self_t, w_neigh_t, d_self * d_out, d_neigh * d_out, wscale);
+      GR_LAUNCH_CHECK();
+      const int total = (d_neigh + d_self) / 16 * (d_out / 8) * 32;
+      pack_weights_f16_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, wscale,
+                                                                   reinterpret_cast<uint4*>(packed));
+      GR_LAUNCH_CHECK();
+    } else {
       const int total = (d_neigh + d_self) / 8 * (d_out / 8) * 32;
       pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, packed);
       GR_LAUNCH_CHECK();
-      p.packed = packed;
     }
+    p.packed = packed;
+    p.wscale = wscale;
     int rc;
     const int vn = (d_neigh + 127) / 128;
     if (maxr) rc = vn == 1 ? launch_long_rows<1, true>(indptr, indices, edge_w_or_null, h_src, d_neigh, row_begin, row_end, lw, st)
@@ -632,7 +808,8 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
                       : launch_long_rows<2, false>(indptr, indices, edge_w_or_null, h_src, d_neigh, row_begin, row_end, lw, st);
     if (rc != GR_OK) return rc;
     bool handled = false;
-    rc = maxr ? dispatch_fused<true>(p, lw, st, &handled) : dispatch_fused<false>(p, lw, st, &handled);
+    if (f16) rc = maxr ? dispatch_fused<true, true>(p, lw, st, &handled) : dispatch_fused<false, true>(p, lw, st, &handled);
+    else rc = maxr ? dispatch_fused<true, false>(p, lw, st, &handled) : dispatch_fused<false, false>(p, lw, st, &handled);
     if (rc != GR_OK) return rc;
     if (handled) return GR_OK;
   }

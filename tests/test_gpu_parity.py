@@ -228,36 +228,49 @@ def test_gather_reduce_vs_oracle(grb, d, reducer):
         np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize('dims', [(128, 128, 128), (256, 256, 256), (256, 256, 128), (128, 128, 64), (4, 2, 16), (100, 60, 36)])
+@pytest.mark.parametrize('epilogue', [1, 0], ids=['f16x3', 'tf32x3'])
+@pytest.mark.parametrize('dims', [(128, 128, 128), (256, 256, 256), (256, 256, 128), (128, 128, 64), (4, 2, 16), (100, 60, 36),
+                                  (120, 120, 64)])
 @pytest.mark.parametrize('agg', ['mean', 'pool_nn'])
-def test_sage_relation_vs_oracle(grb, dims, agg):
+def test_sage_relation_vs_oracle(grb, dims, agg, epilogue):
+    lib = grb._native.load()
+    lib.gr_sage_epilogue_mode(epilogue)
+    try:
+        for scale, l2 in ((1.0, True), (3e4, True), (1e-5, False)):  # the fp16 epilogue must not care about the input scale
+            _sage_relation(grb, dims, agg, scale, l2)
+    finally:
+        lib.gr_sage_epilogue_mode(1)
+
+
+def _sage_relation(grb, dims, agg, in_scale, l2norm):
     dn, ds, dout = dims
     rng = np.random.default_rng(dn + dout)
     n_src, n_dst, nnz = 2000, 1111, 30000
     src, dst, indptr, indices, eperm = random_csr(rng, n_src, n_dst, nnz, hub=5000)
     dst[dst == 7] = 8  # an isolated destination row
     indptr, indices, eperm = O.csr_by_dst(src, dst, n_dst)
-    hs = torch.from_numpy(np.abs(rng.standard_normal((n_src, dn))).astype(np.float32))
-    hd = torch.from_numpy(rng.standard_normal((n_dst, ds)).astype(np.float32))
+    hs = torch.from_numpy(np.abs(rng.standard_normal((n_src, dn))).astype(np.float32)) * in_scale
+    hd = torch.from_numpy(rng.standard_normal((n_dst, ds)).astype(np.float32)) * in_scale
     hd[3] = 0
     ws = torch.from_numpy((rng.standard_normal((dout, ds)) / np.sqrt(ds)).astype(np.float32))
     wn = torch.from_numpy((rng.standard_normal((dout, dn)) / np.sqrt(dn)).astype(np.float32))
     dev = 'cuda:0'
-    want = O.conv_layer(torch.from_numpy(src), torch.from_numpy(dst), None, hs, hd, ws, wn, None, 'mean', True)
+    want = O.conv_layer(torch.from_numpy(src), torch.from_numpy(dst), None, hs, hd, ws, wn, None, 'mean', l2norm)
     if agg == 'pool_nn':
-        want = O.conv_layer(torch.from_numpy(src), torch.from_numpy(dst), None, hs, hd, ws, wn, torch.eye(dn), 'pool_nn', True)
+        want = O.conv_layer(torch.from_numpy(src), torch.from_numpy(dst), None, hs, hd, ws, wn, torch.eye(dn), 'pool_nn', l2norm)
     out = torch.empty(n_dst, dout, device=dev)
     red = 1 if agg == 'pool_nn' else 0
     args = (torch.from_numpy(indptr).to(dev), torch.from_numpy(indices).to(dev), None, hs.to(dev), hd.to(dev),
             ws.t().contiguous().to(dev), wn.t().contiguous().to(dev))
-    grb.ops.sage_relation(*args, out, red, True)
-    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+    atol = ATOL if l2norm else ATOL * in_scale * 10
+    grb.ops.sage_relation(*args, out, red, l2norm)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=RTOL, atol=atol)
     # accumulate modes and a destination shard
-    grb.ops.sage_relation(*args, out, red, True, grb._native.ACC_ADD, 0.5)
-    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)  # (z + z) * 0.5
+    grb.ops.sage_relation(*args, out, red, l2norm, grb._native.ACC_ADD, 0.5)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=RTOL, atol=atol)  # (z + z) * 0.5
     out2 = torch.full((n_dst, dout), -7.0, device=dev)
-    grb.ops.sage_relation(*args, out2, red, True, row_begin=100, row_end=900)
-    np.testing.assert_allclose(out2[100:900].cpu().numpy(), want[100:900].numpy(), rtol=RTOL, atol=ATOL)
+    grb.ops.sage_relation(*args, out2, red, l2norm, row_begin=100, row_end=900)
+    np.testing.assert_allclose(out2[100:900].cpu().numpy(), want[100:900].numpy(), rtol=RTOL, atol=atol)
     assert bool((out2[:100] == -7).all()) and bool((out2[900:] == -7).all())
 
 
