@@ -265,7 +265,8 @@ def main():
         if world == 1:
             h = model.get_repr(blocks, h)
         else:
-            h = D.sharded_get_repr(model, blocks, h, gather_last=('item',) if args.item_shards == 1 else None)
+            h = D.sharded_get_repr(model, blocks, h, gather_last=('item',) if args.item_shards == 1 else None,
+                                   balance=('item',) if args.item_shards == 1 else ())
         mark('aggregate')
         if world == 1:
             table = grb.ScoringTable(h['item'], cfg)
@@ -292,7 +293,8 @@ def main():
             ids = grb.get_recs_tensor(g, y, K_RECS, uid_all, bought, True, dev, config=cfg)
         else:
             h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
-            h = D.sharded_get_repr(model, blocks, model.embed(h), gather_last=('item',) if args.item_shards == 1 else None)
+            h = D.sharded_get_repr(model, blocks, model.embed(h), gather_last=('item',) if args.item_shards == 1 else None,
+                                   balance=('item',) if args.item_shards == 1 else ())
             ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, item_shards=args.item_shards)
         host_ids = ids_pinned[:ids.shape[0]]
         host_ids.copy_(ids, non_blocking=True)

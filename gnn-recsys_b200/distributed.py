@@ -56,6 +56,59 @@ def allgather_rows(local_full: torch.Tensor, n: int, group=None) -> torch.Tensor
     return full[:n]
 
 
+def balanced_bounds(block, ntype: str, world: int, row_cost: int = 8):
+    """Contiguous destination ranges of ``ntype`` with (nearly) equal WORK instead of equal row counts: boundaries
+    sit on the prefix sum of ``in-degree over all relations into ntype + row_cost`` (the fused kernel's cost per row
+    is its gathered edges plus a fixed projection epilogue). With Zipf item popularity one hub row can hold several
+    per cent of all edges, so equal row ranges leave the hub's rank far behind. Returns ``world + 1`` ints; cached on
+    the block."""
+    cache = block.__dict__.setdefault('_balanced_bounds', {})
+    key = (ntype, world, row_cost)
+    if key not in cache:
+        n = block.number_of_dst_nodes(ntype)
+        cost = None
+        for c, rel in block.rels.items():
+            if c[2] != ntype or rel.nnz == 0:
+                continue
+            deg = (rel.indptr[1:] - rel.indptr[:-1]).to(torch.int64)
+            cost = deg if cost is None else cost + deg
+        if cost is None or n == 0:
+            cache[key] = [shard_range(n, world, r)[0] for r in range(world)] + [n]
+        else:
+            pref = torch.cumsum(cost + row_cost, 0)
+            targets = (pref[-1].double() * torch.arange(1, world, dtype=torch.float64, device=pref.device) / world)
+            cuts = torch.searchsorted(pref.double(), targets).clamp_(max=n).cpu().tolist()
+            b = [0] + [int(x) for x in cuts] + [n]
+            for i in range(1, len(b)):  # monotone (a hub heavier than a fair share empties its neighbours' ranges)
+                b[i] = max(b[i], b[i - 1])
+            cache[key] = b
+    return cache[key]
+
+
+def allgather_rows_v(local_full: torch.Tensor, bounds, group=None) -> torch.Tensor:
+    """``allgather_rows`` for unequal contiguous ranges ``bounds`` (``world + 1`` ints): every rank contributes rows
+    ``[bounds[rank], bounds[rank + 1])`` of its ``local_full``; chunks are padded to the longest range for one
+    ``all_gather_into_tensor`` and copied back into place."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return local_full
+    sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+    c = max(max(sizes), 1)
+    buf = local_full.new_empty((world * c, local_full.shape[1]))
+    mine = buf[rank * c:(rank + 1) * c]
+    mine[:sizes[rank]].copy_(local_full[bounds[rank]:bounds[rank + 1]])
+    if dist.get_backend(group) == 'gloo':
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous(), group=group)
+        buf = torch.cat(parts, 0)
+    else:
+        dist.all_gather_into_tensor(buf, mine, group=group)
+    for r in range(world):
+        if r != rank and sizes[r]:
+            local_full[bounds[r]:bounds[r + 1]].copy_(buf[r * c:r * c + sizes[r]])
+    return local_full
+
+
 def exchange_topk(ids: torch.Tensor, scores: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor, int, int]:
     """``ids`` / ``scores``: ``[n_users, k]`` per-shard top-k of ALL users on this rank. Sends each user range to its
     owner; returns ``(ids [world, chunk, k], scores [world, chunk, k], begin, end)`` for this rank's user range
@@ -76,18 +129,28 @@ def exchange_topk(ids: torch.Tensor, scores: torch.Tensor, group=None) -> Tuple[
     return out_ids.view(world, c, k), out_scores.view(world, c, k), b, e
 
 
-def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None, gather_last=None) -> Dict[str, torch.Tensor]:
+def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None, gather_last=None,
+                     balance=()) -> Dict[str, torch.Tensor]:
     """``ConvModel.get_repr`` with destination-range sharding. Every layer output is all-gathered (the next layer
     gathers arbitrary source rows); ``gather_last`` (a collection of node types, default: all) limits the all-gather
-    after the LAST layer -- a table that is not gathered comes back full-height with only this rank's
-    ``shard_range`` rows valid (user-range-sharded scoring needs nothing else of the user table)."""
+    after the LAST layer -- a table that is not gathered comes back full-height with only this rank's rows valid
+    (user-range-sharded scoring needs nothing else of the user table). Node types in ``balance`` are cut by
+    ``balanced_bounds`` (equal work), the others by ``shard_range`` (equal rows -- the ranges scoring shards by)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     for i, blk in enumerate(blocks):
-        ranges = {t: shard_range(blk.number_of_dst_nodes(t), world, rank) for t in blk.dsttypes}
+        bounds = {t: balanced_bounds(blk, t, world) for t in blk.dsttypes if t in balance}
+        ranges = {t: ((bounds[t][rank], bounds[t][rank + 1]) if t in bounds else
+                      shard_range(blk.number_of_dst_nodes(t), world, rank)) for t in blk.dsttypes}
         out = model.layers[i](blk, h, ranges)
         last = i == len(blocks) - 1
-        h = {t: (allgather_rows(v, v.shape[0], group) if (not last or gather_last is None or t in gather_last) else v)
-             for t, v in out.items()}
+        h = {}
+        for t, v in out.items():
+            if last and gather_last is not None and t not in gather_last:
+                h[t] = v
+            elif t in bounds:
+                h[t] = allgather_rows_v(v, bounds[t], group)
+            else:
+                h[t] = allgather_rows(v, v.shape[0], group)
     return h
 
 

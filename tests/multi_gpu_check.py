@@ -35,6 +35,12 @@ def main():
             hs = D.sharded_get_repr(model, blocks, model.embed(dict(feats)))
         for t in h1:
             assert torch.equal(h1[t], hs[t]), 'sharded embeddings differ for %s (%s)' % (t, agg)  # same kernels, same order
+        with torch.no_grad():
+            hb = D.sharded_get_repr(model, blocks, model.embed(dict(feats)), balance=('item', 'user'))
+        for t in h1:
+            assert torch.equal(h1[t], hb[t]), 'work-balanced sharding differs for %s (%s)' % (t, agg)
+        bi = D.balanced_bounds(blk, 'item', world)
+        assert bi[0] == 0 and bi[-1] == data.n_items and all(a <= b for a, b in zip(bi, bi[1:]))
         buys = data.relations()[('user', 'buys', 'item')]
         bought = grb.BoughtCSR.from_edges(buys[0], buys[1], data.n_users)
         ids1, sc1 = grb.recommend_topk(h1['user'], grb.ScoringTable(h1['item'], grb.RecsConfig()), 10, bought)

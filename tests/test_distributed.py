@@ -33,6 +33,11 @@ def _worker(rank, world, port, n_users, n_items, k, ret):
         local[b:e] = full[b:e]
         out = D.allgather_rows(local, n_users)
         assert torch.equal(out, full)
+        # unequal contiguous ranges (work-balanced sharding)
+        bounds = [0, n_users // 5, n_users] if world == 2 else [0] + [n_users * (r + 1) // world for r in range(world)]
+        local = torch.full((n_users, 8), float('nan'))
+        local[bounds[rank]:bounds[rank + 1]] = full[bounds[rank]:bounds[rank + 1]]
+        assert torch.equal(D.allgather_rows_v(local, bounds), full)
         # ---- per-shard exact top-k of ALL users (oracle on this rank's item range) -> owner-side merge
         hu = torch.nn.functional.normalize(torch.rand(n_users, 16, generator=g), dim=1)
         hi = torch.nn.functional.normalize(torch.rand(n_items, 16, generator=g), dim=1)
@@ -80,3 +85,19 @@ def test_shard_ranges_cover_and_are_contiguous():
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
             assert all(e - b <= D.chunk_rows(n, world) for b, e in rs)
+
+
+def test_balanced_bounds_equalise_work():
+    import gnn_recsys_b200 as grb
+    D = grb.distributed
+    d = grb.make_graph(500, 200, 20000, seed=2)
+    d.items[:4000] = 3  # a hub item with 20 % of all edges
+    blk = d.graph().full_block()
+    for world in (2, 4, 8):
+        b = D.balanced_bounds(blk, 'item', world)
+        assert b[0] == 0 and b[-1] == 200 and all(x <= y for x, y in zip(b, b[1:]))
+        deg = sum((blk.rels[c].indptr[1:] - blk.rels[c].indptr[:-1]).long() for c in blk.rels if c[2] == 'item') + 8
+        work = [int(deg[b[r]:b[r + 1]].sum()) for r in range(world)]
+        equal = [int(deg[s:e].sum()) for s, e in (D.shard_range(200, world, r) for r in range(world))]
+        assert max(work) <= max(equal)
+        assert max(work) <= max(int(deg.max()), int(deg.sum()) // world + int(deg.max()))
