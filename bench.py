@@ -66,7 +66,7 @@ class ClockSampler:
         self.lines, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -306,6 +306,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi starts BEFORE the warm-up: its start-up (NVML init) stalls kernel launches for milliseconds, which
+    # must not land in the timed region (it showed up as a 6 ms "aggregate" stage on the 2 ms c1 step)
+    sampler = ClockSampler(local) if rank == 0 else None
+
     # ---- warm-up (also the verification pass)
     for _ in range(max(args.warmup, 1)):
         ids, n_over, h = resident_step()
@@ -331,7 +335,6 @@ def main():
     # ---- timed: resident inputs, CUDA events, max over ranks
     launches0 = N.kernel_launches()
     rec = []
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     w0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
