@@ -166,7 +166,32 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
       id = sl_id[u * S + lane];
       approx = sl_score[u * S + lane];
     }
-    if (id >= 0) {
+    if ((d & 31) == 0) {
+      // 8 lanes per candidate, 4 candidates per pass: every load instruction covers 4 x 128 contiguous bytes
+      // (the one-lane-per-candidate walk touched 32 different rows per instruction, half a sector each)
+      const int grp = lane >> 3, sub = lane & 7;
+      for (int pass = 0; pass * 4 < S; ++pass) {
+        const int cid = __shfl_sync(FULL, id, min(pass * 4 + grp, 31));
+        float dot = 0.f, ni = 0.f;
+        if (cid >= 0 && pass * 4 + grp < S) {
+          const float* row = hi + (cid - item_id_base) * (long long)d;
+          for (int c = sub * 4; c < d; c += 32) {
+            const float4 x = *reinterpret_cast<const float4*>(xu + c);
+            const float4 y = gr::ldg_f4(row + c);
+            dot = fmaf(x.x, y.x, dot); dot = fmaf(x.y, y.y, dot); dot = fmaf(x.z, y.z, dot); dot = fmaf(x.w, y.w, dot);
+            ni = fmaf(y.x, y.x, ni); ni = fmaf(y.y, y.y, ni); ni = fmaf(y.z, y.z, ni); ni = fmaf(y.w, y.w, ni);
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(FULL, dot, o);
+          ni += __shfl_xor_sync(FULL, ni, o);
+        }
+        const float eg = cosine(dot, nu, ni, eps);
+        const float mine = __shfl_sync(FULL, eg, (lane & 3) * 8);  // candidate `lane` was handled by group lane % 4
+        if ((lane >> 2) == pass && id >= 0) e = mine;
+      }
+    } else if (id >= 0) {
       float dot, ni;
       dot_norm(xu, hi + (id - item_id_base) * (long long)d, d, dot, ni);
       e = cosine(dot, nu, ni, eps);
