@@ -398,27 +398,48 @@ struct SageParams {
   float* out;
   const float4* packed;  // pre-split weights in B-fragment order (fused kernel only)
   const float* wscale;   // fp16 variant: {2^p, 2^-p} applied to the weights
+  int* tile_counter;     // zero-initialised; groups take tiles from it
 };
 
 constexpr int PAD_TF32 = 4, PAD_F16 = 8;  // floats of row padding: conflict-free 32-bit / 64-bit fragment loads
 
-// MT = 16-row m-tiles per warp (tile rows R = 32 * MT: two row groups), NT = 8-column n-tiles per warp
-// (d_out = 32 * NT: four column groups). VN / VS = float4 per lane of a neighbour / self row.
+// A CTA is two independent GROUPS of four warps (named barriers); each group walks its own sequence of R-row tiles
+// (R = 16 * MT) taken from a global counter: gather phase (LSU / L2 bound) -> projection phase (tensor bound). The six
+// groups resident on an SM drift apart, so one group's gather overlaps another group's MMAs -- with one 8-warp tile per
+// CTA the three resident CTAs ran in lockstep and the two phases simply added up.
+// MT = 16-row m-tiles per warp, NT = 8-column n-tiles per warp (d_out = 32 * NT: the four warps of a group split the
+// columns). VN / VS = float4 per lane of a neighbour / self row.
+constexpr int GROUP_THREADS = 128;
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GROUP_THREADS) : "memory");
+}
 template <int VN, int VS, int NT, int MT, bool MAXR, bool F16>
 __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fused_kernel(SageParams p, LongWs lw) {
-  constexpr int R = 32 * MT;
+  constexpr int R = 16 * MT;
   constexpr int PAD = F16 ? PAD_F16 : PAD_TF32;
   extern __shared__ __align__(16) float smem[];
   const int pn = p.dn + PAD, ps = p.ds + PAD;
-  float* sN = smem;            // [R][dn + PAD]
-  float* sS = smem + R * pn;   // [R][ds + PAD]
-  __shared__ int s_next;
-  __shared__ float s_part[4][R];
-  __shared__ float s_inv[R];  // F16: 1 / row scale
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row0 = p.row_begin + (int64_t)blockIdx.x * R;
-  if (threadIdx.x == 0) s_next = 0;
-  __syncthreads();
+  const int grp = warp >> 2;                     // group of 4 warps
+  float* sN = smem + grp * R * (pn + ps);        // [R][dn + PAD]
+  float* sS = sN + R * pn;                       // [R][ds + PAD]
+  __shared__ int s_next_[2], s_tile_[2];
+  __shared__ float s_part_[2][4][R];
+  __shared__ float s_inv_[2][R];                 // F16: 1 / row scale
+  int& s_next = s_next_[grp];
+  float (&s_part)[4][R] = s_part_[grp];
+  float (&s_inv)[R] = s_inv_[grp];
+  const int64_t n_tiles_total = (p.row_end - p.row_begin + R - 1) / R;
+
+ for (;;) {  // persistent: one tile per iteration and group
+  if ((threadIdx.x & (GROUP_THREADS - 1)) == 0) {
+    s_tile_[grp] = atomicAdd(p.tile_counter, 1);
+    s_next = 0;
+  }
+  group_sync(grp);
+  const int64_t tile = s_tile_[grp];
+  if (tile >= n_tiles_total) break;
+  const int64_t row0 = p.row_begin + tile * R;
 
   // phase 1: warps pull rows of the tile dynamically (degree skew), gather -> smem
   while (true) {
@@ -461,10 +482,10 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
       for (int c = lane * 4; c < p.ds; c += 128) *reinterpret_cast<float4*>(sS + r * ps + c) = make_float4(0, 0, 0, 0);
     }
   }
-  __syncthreads();
+  group_sync(grp);
 
-  // phase 2: z = relu([S | N] . [Ws^T ; Wn^T]) on the tensor cores (3xTF32)
-  const int rg = warp & 1, cg = warp >> 1;          // row group (R / 2 rows), column group (d_out / 4 columns)
+  // phase 2: z = relu([S | N] . [Ws^T ; Wn^T]) on the tensor cores (hi/lo split, 3 products)
+  const int cg = warp & 3;                          // column group (d_out / 4 columns); every warp covers all R rows
   const int g = lane >> 2, tig = lane & 3;
   const int n_tiles = p.dout / 8;
   const int ks_self = p.ds / 8, ks_all = (p.ds + p.dn) / 8;
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
       const int kc = (ks < ks16_self ? ks : ks - ks16_self) * 16 + 2 * tig;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const float* a = tile + (rg * (R / 2) + m * 16 + g) * pitch + kc;
+        const float* a = tile + (m * 16 + g) * pitch + kc;
         const float2 x0 = *reinterpret_cast<const float2*>(a), x1 = *reinterpret_cast<const float2*>(a + 8 * pitch);
         const float2 x2 = *reinterpret_cast<const float2*>(a + 8), x3 = *reinterpret_cast<const float2*>(a + 8 * pitch + 8);
         uint32_t ah[4], al[4];
@@ -528,7 +549,7 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
     const int kc = (ks < ks_self ? ks : ks - ks_self) * 8 + tig;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const float* a = tile + (rg * (R / 2) + m * 16 + g) * pitch + kc;
+      const float* a = tile + (m * 16 + g) * pitch + kc;
       uint32_t ah[4], al[4];
       split_tf32(a[0], ah[0], al[0]);
       split_tf32(a[8 * pitch], ah[1], al[1]);
@@ -567,15 +588,15 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
         float v = ss[m][h];
         v += __shfl_xor_sync(FULL, v, 1);
         v += __shfl_xor_sync(FULL, v, 2);
-        if (tig == 0) s_part[cg][rg * (R / 2) + m * 16 + h * 8 + g] = v;
+        if (tig == 0) s_part[cg][m * 16 + h * 8 + g] = v;
       }
-    __syncthreads();
+    group_sync(grp);
   }
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int r = rg * (R / 2) + m * 16 + h * 8 + g;
+      const int r = m * 16 + h * 8 + g;
       const int64_t row = row0 + r;
       float nrm = 1.f;
       if (p.l2norm) {
@@ -603,6 +624,8 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
       }
     }
   }
+  group_sync(grp);  // the next tile overwrites this group's shared memory
+ }
 }
 
 // ------------------------------------------------------------------------------------------------ generic dims
@@ -709,14 +732,16 @@ int launch_long_rows(const int* indptr, const int* indices, const float* ew, con
 
 template <int VN, int VS, int NT, int MT, bool MAXR, bool F16>
 int launch_fused(const SageParams& p, const LongWs& lw, cudaStream_t st) {
-  constexpr int R = 32 * MT;
-  const size_t smem = sizeof(float) * R * (p.dn + p.ds + 2 * (F16 ? PAD_F16 : PAD_TF32));
+  constexpr int R = 16 * MT;
+  const size_t smem = sizeof(float) * 2 * R * (p.dn + p.ds + 2 * (F16 ? PAD_F16 : PAD_TF32));
   auto kern = sage_fused_kernel<VN, VS, NT, MT, MAXR, F16>;
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int64_t rows = p.row_end - p.row_begin;
   const int64_t tiles = (rows + R - 1) / R;
-  kern<<<(unsigned)tiles, THREADS, smem, st>>>(p, lw);
+  const int per_sm = (VN == 1 && NT <= 4) ? 3 : 2;
+  const int64_t grid = std::min<int64_t>((tiles + 1) / 2, (int64_t)gr::sm_count() * per_sm);
+  kern<<<(unsigned)std::max<int64_t>(grid, 1), THREADS, smem, st>>>(p, lw);
   GR_LAUNCH_CHECK();
   return GR_OK;
 }
@@ -774,7 +799,7 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
   GR_REQUIRE(nnz == 0 || indices, GR_E_INVALID, "null indices");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SageParams p{indptr, indices, edge_w_or_null, h_src, h_dst, row_begin, row_end, d_neigh, d_self, d_out,
-               w_self_t, w_neigh_t, l2norm, accumulate, z_scale, out, nullptr, nullptr};
+               w_self_t, w_neigh_t, l2norm, accumulate, z_scale, out, nullptr, nullptr, nullptr};
   const bool maxr = reducer == GR_REDUCE_MAX;
   LongWs lw{};
   if (fast_dims(d_neigh, d_self, d_out)) {
@@ -800,6 +825,7 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
     }
     p.packed = packed;
     p.wscale = wscale;
+    p.tile_counter = lw.counters + 2;  // zeroed by launch_long_rows below (it clears all 256 bytes of counters)
     int rc;
     const int vn = (d_neigh + 127) / 128;
     if (maxr) rc = vn == 1 ? launch_long_rows<1, true>(indptr, indices, edge_w_or_null, h_src, d_neigh, row_begin, row_end, lw, st)
