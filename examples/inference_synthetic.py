@@ -42,7 +42,8 @@ def main():
 
     user_ids = np.arange(args.users)
     sampler = dgl.MultiLayerFullNeighborSampler(args.n_layers - 1)
-    loader = dgl.NodeDataLoader(graph, {'user': user_ids, 'item': np.arange(args.items)}, sampler, batch_size=None)
+    loader = dgl.NodeDataLoader(graph, {'user': user_ids, 'item': np.arange(args.items)}, sampler, batch_size=128, shuffle=True,
+                                drop_last=False, num_workers=0)   # main_inference.py:130-138
     t0 = time.perf_counter()
     embeddings = get_embeddings(graph, dim_dict['out'], model, loader, len(loader), True, device, True)
     torch.cuda.synchronize()

@@ -149,17 +149,21 @@ class MultiLayerNeighborSampler(_FrontierSampler):
 class NodeDataLoader:
     """``dgl.dataloading.NodeDataLoader`` surface: iterate ``(input_nodes, output_nodes, blocks)``.
 
-    ``batch_size=None`` (or >= number of seeds) with a full-neighbour sampler takes the fast path: one
-    iteration whose blocks are full-graph blocks; ``get_embeddings`` then keeps only the seeded rows.
+    With a full-neighbour sampler the embedding of a seed node does not depend on the batch it is computed in, so
+    the loader takes the fast path whatever ``batch_size`` says (the reference passes 128, ``main_inference.py:134``):
+    ONE iteration whose blocks are full-graph blocks; ``get_embeddings`` then keeps only the seeded rows.
+    ``force_minibatch=True`` restores the reference's batching (sampled blocks per ``batch_size`` seeds) -- it only
+    differs when a mini-batch happens to contain no edge of some relation.
     """
 
     def __init__(self, g: HeteroGraph, nids, block_sampler, batch_size=None, shuffle=False, drop_last=False,
-                 num_workers=0, seed=0, edge_weight=None, **kwargs):
+                 num_workers=0, seed=0, edge_weight=None, force_minibatch=False, **kwargs):
         self.g, self.sampler = g, block_sampler
         self.nids = {t: _as_np_ids(v).astype(np.int64) for t, v in nids.items()}
         self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
         self.rng = np.random.default_rng(seed)
         self.edge_weight = edge_weight
+        self.force_minibatch = force_minibatch
         self._flat_t = np.concatenate([np.full(v.size, i) for i, (t, v) in enumerate(sorted(self.nids.items()))]) \
             if self.nids else np.zeros(0, np.int64)
         self._flat_i = np.concatenate([v for _, v in sorted(self.nids.items())]) if self.nids else np.zeros(0, np.int64)
@@ -167,12 +171,12 @@ class NodeDataLoader:
 
     @property
     def full_graph(self) -> bool:
-        return (self.batch_size is None or self.batch_size >= self._flat_i.size) and \
-            isinstance(self.sampler, MultiLayerFullNeighborSampler)
+        return isinstance(self.sampler, MultiLayerFullNeighborSampler) and (
+            not self.force_minibatch or self.batch_size is None or self.batch_size >= self._flat_i.size)
 
     def __len__(self):
         n = self._flat_i.size
-        if self.batch_size is None:
+        if self.batch_size is None or self.full_graph:
             return 1
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 

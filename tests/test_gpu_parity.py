@@ -65,7 +65,11 @@ def test_embeddings_minibatch_loader(grb, name):
     model = product_model(grb, g, meta, z, dev)
     conv = meta['n_layers'] - 1 if meta['embedding_layer'] else meta['n_layers']
     nids = {'user': z['user_ids'], 'item': np.arange(meta['n_items'])}
-    loader = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(conv), batch_size=32, shuffle=True, seed=5)
+    loader = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(conv), batch_size=32, shuffle=True, seed=5,
+                                force_minibatch=True)
+    assert not loader.full_graph and len(loader) > 1
+    ref_style = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(conv), batch_size=128, shuffle=True)
+    assert ref_style.full_graph and len(ref_style) == 1  # the reference's own call shape takes the one-pass path
     y = grb.get_embeddings(g, meta['out'], model, loader, len(loader), False, dev, meta['embedding_layer'])
     for t in ('user', 'item'):
         assert not y[t].is_cuda

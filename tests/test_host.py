@@ -61,7 +61,7 @@ def test_full_block_and_minibatch_blocks_agree_with_oracle_embeddings():
     feats = {'user': d.user_feat, 'item': d.item_feat}
     want = O.get_embeddings_full(num, [blk, blk], feats, sd, 8)
     loader = grb.NodeDataLoader(g, {'user': np.arange(60), 'item': np.arange(25)}, grb.MultiLayerFullNeighborSampler(2),
-                                batch_size=16, shuffle=True, seed=1)
+                                batch_size=16, shuffle=True, seed=1, force_minibatch=True)
     assert len(loader) == 6 and not loader.full_graph
     got = {t: torch.zeros(n, 8) for t, n in num.items()}
     for _, out_nodes, blocks in loader:
