@@ -81,12 +81,13 @@ def get_recs(g, h, model, embed_dim, k, user_ids, already_bought_dict, remove_al
     ids = get_recs_tensor(g, h, k, user_ids, already_bought_dict, remove_already_bought, device,
                           use_popularity=use_popularity, weight_popularity=weight_popularity).cpu().numpy()
     ids = ids.astype(np.int64)
-    recs = {}
-    for r, user in enumerate(user_ids):
-        row = ids[r]
-        row = row[row >= 0]
-        recs[user] = list(row) if remove_already_bought else row
-    return recs
+    if not remove_already_bought:  # the reference returns the ndarray slice order[:k] on this branch
+        return {user: ids[r][ids[r] >= 0] for r, user in enumerate(user_ids)}
+    rows = ids.tolist()
+    short = np.nonzero((ids < 0).any(axis=1))[0]  # users with fewer than k candidates (rare): drop the padding
+    for r in short.tolist():
+        rows[r] = [i for i in rows[r] if i >= 0]
+    return dict(zip(list(user_ids), rows))
 
 
 def create_ground_truth(users, items):

@@ -423,3 +423,34 @@ def _recs_large(grb, shape):
     for r in sample[:200]:
         assert not set(ids[r].tolist()) & set(bought[r])
     assert int(n_over) <= n_u
+
+
+def test_empty_inputs_and_empty_relations(grb):
+    """Edge cases of the reference semantics: no users / no items; a relation without edges is skipped by
+    HeteroGraphConv and a destination type that receives nothing is absent from the layer output."""
+    dev = torch.device('cuda:0')
+    hi = torch.rand(50, 128, device=dev)
+    table = grb.ScoringTable(hi, grb.RecsConfig())
+    ids, sc = grb.recommend_topk(torch.zeros(0, 128, device=dev), table, 10)
+    assert tuple(ids.shape) == (0, 10)
+    ids, sc = grb.recommend_topk(torch.rand(7, 128, device=dev), grb.ScoringTable(torch.zeros(0, 128, device=dev), grb.RecsConfig()), 10)
+    assert tuple(ids.shape) == (7, 10) and bool((ids == -1).all())
+    ids, sc = grb.recommend_topk(torch.rand(7, 128, device=dev), grb.ScoringTable(hi[:4], grb.RecsConfig()), 10)
+    assert bool((ids[:, :4] >= 0).all()) and bool((ids[:, 4:] == -1).all())   # fewer items than k
+    # zero user rows score 0 against everything: any 10 distinct items are a valid answer
+    ids, sc = grb.recommend_topk(torch.zeros(3, 128, device=dev), table, 10)
+    assert bool((sc == 0).all()) and all(len(set(r.tolist())) == 10 for r in ids)
+    # graph: only 'buys' has edges; 'clicks' / 'clicked-by' / 'bought-by' are empty
+    e = (np.array([0, 1, 2, 2]), np.array([1, 1, 0, 3]))
+    z0 = (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    g = grb.HeteroGraph({RELS[2]: e, RELS[0]: z0, RELS[1]: z0, RELS[3]: z0}, {'user': 4, 'item': 5})
+    model = grb.ConvModel(g, 2, {'user': 2, 'item': 4, 'hidden': 16, 'out': 8}).to(dev).eval()
+    blk = g.full_block_on(dev)
+    h = model.embed({'user': torch.rand(4, 2, device=dev), 'item': torch.rand(5, 4, device=dev)})
+    out = model.get_repr([blk], dict(h))
+    assert set(out.keys()) == {'item'} and tuple(out['item'].shape) == (5, 8)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    want = O.get_repr([O.block_from_coo({'user': 4, 'item': 5}, {'user': 4, 'item': 5},
+                                        {RELS[2]: (e[0], e[1], None), RELS[0]: (z0[0], z0[1], None)})],
+                      {t: v.cpu() for t, v in h.items()}, sd)
+    np.testing.assert_allclose(out['item'].cpu().numpy(), want['item'].numpy(), rtol=RTOL, atol=ATOL)
