@@ -454,3 +454,26 @@ def test_empty_inputs_and_empty_relations(grb):
                                         {RELS[2]: (e[0], e[1], None), RELS[0]: (z0[0], z0[1], None)})],
                       {t: v.cpu() for t, v in h.items()}, sd)
     np.testing.assert_allclose(out['item'].cpu().numpy(), want['item'].numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_duplicate_items_overflow_path_and_fp16_never_overflows(grb):
+    """An item table made of exact duplicates (cold-start items with identical features): every shortlist is one big
+    tie. With tie_tol = 0 the proof must fail for every user and the exact fp32 fallback must still return a correct
+    answer; with the default tolerance the fp16 split (2 * err < 1e-5) can never overflow."""
+    rng = np.random.default_rng(5)
+    dev = 'cuda:0'
+    base = clustered_embeddings(rng, 20, 128, 0.3)
+    hi = base.repeat_interleave(100, dim=0)[torch.from_numpy(rng.permutation(2000))].contiguous()
+    hu = clustered_embeddings(rng, 600, 128, 0.3)
+    scores = O.get_recs_scores(hu, hi, np.arange(600)).numpy()
+    want = O.get_recs_vectorised(hu, hi, 10, np.arange(600))
+    strict = grb.RecsConfig(elem='bf16', parts=2, tie_tol=0.0)
+    ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), strict), 10, None, return_overflow=True)
+    assert int(n_over) == 600                                  # 100-fold ties: nothing can be proven at tolerance 0
+    assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
+    for elem in ('fp16', 'bf16'):
+        cfg = grb.RecsConfig(elem=elem, parts=2)
+        ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), cfg), 10, None, return_overflow=True)
+        assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
+        if elem == 'fp16':
+            assert int(n_over) == 0
