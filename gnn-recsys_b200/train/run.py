@@ -40,6 +40,7 @@ def get_embeddings(g, out_dim: int, trained_model, nodeloader_test, num_batches_
             blocks = [blk] * len(blocks)
             input_features = {t: g.nodes[t].data['features'].to(dev, torch.float32, non_blocking=True)
                               for t in g.ntypes if 'features' in g.nodes[t].data}
+            output_nodes = {t: v for t, v in output_nodes.items()}
         else:
             blocks = [b.to(dev) for b in blocks]
             input_features = {t: v.to(dev, torch.float32) for t, v in blocks[0].srcdata['features'].items()}
@@ -50,6 +51,8 @@ def get_embeddings(g, out_dim: int, trained_model, nodeloader_test, num_batches_
                 input_features['sport'] = trained_model.sport_embed(input_features['sport'])
         h = trained_model.get_repr(blocks, input_features)
         for ntype in h.keys():
+            if ntype not in output_nodes:  # full-graph pass: a type nobody seeded (e.g. 'sport') keeps its zero rows
+                continue
             ids = output_nodes[ntype]
             n = g.num_nodes(ntype)
             if full and _is_arange(ids, n):

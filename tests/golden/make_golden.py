@@ -237,3 +237,62 @@ def main_popularity():
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'popularity':
     main_popularity()
+
+
+SPORT_REL = [('item', 'utilized-for', 'sport'), ('sport', 'utilizes', 'item'), ('user', 'practices', 'sport'),
+             ('sport', 'practiced-by', 'user'), ('sport', 'belongs-to', 'sport'), ('sport', 'includes', 'sport')]
+
+
+def sport_case(name, aggregator, seed, n_layers=3, hidden=16, out=8, n_users=50, n_items=20, n_edges=300, n_sports=6):
+    """The full 10-relation schema with a third node type (src/utils_data.py:204-238, include_sport=True), embedded
+    the way main_inference.py does it: only users and items are seeded, so the 'sport' table stays zero
+    (src/train/run.py:329-333). `_edge` aggregators multiply by `occurrence` on user-item relations only and fall
+    back to copy_src on every relation touching 'sport' (src/model.py:171-208)."""
+    d = tiny_data(n_users, n_items, n_edges, seed)
+    rng = np.random.default_rng(seed + 50)
+    rel = dict(d.relations())
+    i2s = (np.arange(n_items), rng.integers(0, n_sports, n_items))
+    u2s = (rng.integers(0, n_users, 80), rng.integers(0, n_sports, 80))
+    s2g = (np.arange(n_sports), (np.arange(n_sports) + 1) % 3)
+    rel.update({SPORT_REL[0]: i2s, SPORT_REL[1]: (i2s[1], i2s[0]), SPORT_REL[2]: u2s, SPORT_REL[3]: (u2s[1], u2s[0]),
+                SPORT_REL[4]: s2g, SPORT_REL[5]: (s2g[1], s2g[0])})
+    num = {'user': n_users, 'item': n_items, 'sport': n_sports}
+    g = dgl.heterograph({c: (torch.from_numpy(np.asarray(s, dtype=np.int64)), torch.from_numpy(np.asarray(t, dtype=np.int64)))
+                         for c, (s, t) in rel.items()}, num)
+    sport_feat = torch.from_numpy(rng.standard_normal((n_sports, 6)).astype(np.float32))
+    g.nodes['user'].data['features'] = d.user_feat
+    g.nodes['item'].data['features'] = d.item_feat
+    g.nodes['sport'].data['features'] = sport_feat
+    occ = {}
+    if aggregator.endswith('_edge'):
+        nb, nc = int(d.is_buy.sum()), int((~d.is_buy).sum())
+        occ = {'buys': rng.integers(1, 5, nb), 'clicks': rng.integers(1, 5, nc)}
+        occ['bought-by'], occ['clicked-by'] = occ['buys'], occ['clicks']
+        for et, v in occ.items():
+            g.edges[et].data['occurrence'] = torch.from_numpy(v.astype(np.int64))
+    torch.manual_seed(seed + 1)
+    dim_dict = {'user': 2, 'item': 4, 'sport': 6, 'hidden': hidden, 'out': out}
+    model = ConvModel(g, n_layers, dim_dict, True, 0.0, aggregator, 'cos', 'sum', True)
+    model.eval()
+    nids = {'user': torch.arange(n_users), 'item': torch.arange(n_items)}           # main_inference.py:125
+    sampler = dgl.dataloading.MultiLayerFullNeighborSampler(n_layers - 1)
+    loader = dgl.dataloading.NodeDataLoader(g, nids, sampler, batch_size=n_users + n_items, shuffle=False, drop_last=False)
+    with torch.no_grad(), redirect_stdout(io.StringIO()):
+        y = get_embeddings(g, out, model, loader, len(loader), False, None, True)   # reference code
+    assert float(y['sport'].abs().max()) == 0.0
+    arrays = {'sd/' + kk: v for kk, v in model.state_dict().items()}
+    for c, (s, t) in rel.items():
+        arrays['edges/%s/src' % c[1]] = np.asarray(s, dtype=np.int64)
+        arrays['edges/%s/dst' % c[1]] = np.asarray(t, dtype=np.int64)
+    for et, v in occ.items():
+        arrays['occurrence/%s' % et] = v.astype(np.int64)
+    arrays.update({'feat/user': d.user_feat, 'feat/item': d.item_feat, 'feat/sport': sport_feat,
+                   'emb/user': y['user'], 'emb/item': y['item'], 'emb/sport': y['sport']})
+    meta = dict(name=name, num=num, rels=[list(c) for c in rel], n_layers=n_layers, hidden=hidden, out=out,
+                aggregator=aggregator, dims=dim_dict, seed=seed)
+    save_case(name, meta, arrays)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sport':
+    sport_case('sport_mean_edge', 'mean_edge', 21)
+    sport_case('sport_pool_nn', 'pool_nn', 22)

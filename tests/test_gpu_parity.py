@@ -159,6 +159,35 @@ def test_metrics_at_k_match_reference_formula(grb):
     assert grb.recs_to_metrics(recs, truth, g) == (wp, wr, wc)
 
 
+@pytest.mark.parametrize('name', ['sport_mean_edge', 'sport_pool_nn'])
+def test_three_node_type_schema_matches_reference(grb, name):
+    """The reference's full schema (user / item / sport, 10 relations) through the reference's call shape: seeds =
+    users + items only (main_inference.py:125), batch_size 128; the unseeded 'sport' table must come back zero."""
+    meta, z = load_case(name)
+    dev = torch.device('cuda:0')
+    num = meta['num']
+    rels = [tuple(c) for c in meta['rels']]
+    g = grb.HeteroGraph({c: (z['edges/%s/src' % c[1]], z['edges/%s/dst' % c[1]]) for c in rels}, num)
+    for t in num:
+        g.nodes[t].data['features'] = torch.from_numpy(z['feat/' + t])
+    for c in rels:
+        if 'occurrence/%s' % c[1] in z.files:
+            g.edges[c].data['occurrence'] = torch.from_numpy(z['occurrence/%s' % c[1]])
+    model = grb.ConvModel(g, meta['n_layers'], meta['dims'], True, 0.0, meta['aggregator'], 'cos', 'sum', True)
+    assert hasattr(model, 'sport_embed')
+    model.load_state_dict(state_dict(z), strict=True)
+    model = model.to(dev).eval()
+    ew = 'occurrence' if meta['aggregator'].endswith('_edge') else None
+    loader = grb.NodeDataLoader(g, {'user': np.arange(num['user']), 'item': np.arange(num['item'])},
+                                grb.MultiLayerFullNeighborSampler(meta['n_layers'] - 1), batch_size=128, shuffle=True,
+                                drop_last=False, num_workers=0, edge_weight=ew)
+    y = grb.get_embeddings(g, meta['out'], model, loader, len(loader), True, dev, True)
+    assert set(y.keys()) == {'user', 'item', 'sport'}
+    for t in num:
+        np.testing.assert_allclose(y[t].cpu().numpy(), z['emb/' + t], rtol=RTOL, atol=ATOL)
+    assert float(y['sport'].abs().max()) == 0.0
+
+
 def test_forward_scores_and_loss_match_reference(grb):
     meta, z = load_case('fwd_fanout_mean')
     dev = torch.device('cuda:0')

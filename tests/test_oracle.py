@@ -107,3 +107,22 @@ def test_recs_to_metrics_formula():
     truth = {0: [2, 2, 9], 1: [7]}
     p, r, c = O.recs_to_metrics(recs, truth, 10)
     assert p == 1 / 6 and r == 2 / 4 and c == 0.6
+
+
+@pytest.mark.parametrize('name', ['sport_mean_edge', 'sport_pool_nn'])
+def test_three_node_type_schema_matches_reference(name):
+    """10-relation schema with 'sport' nodes (src/utils_data.py:204-238); only users and items are seeded, so the
+    sport table stays zero (run.py:329-333); `_edge` weighting applies to user-item relations only (model.py:173)."""
+    meta, z = load_case(name)
+    num = meta['num']
+    rels = [tuple(c) for c in meta['rels']]
+    coo = {c: (z['edges/%s/src' % c[1]], z['edges/%s/dst' % c[1]],
+               z['occurrence/%s' % c[1]] if 'occurrence/%s' % c[1] in z.files else None) for c in rels}
+    blk = O.block_from_coo(num, num, coo)
+    feats = {t: torch.from_numpy(z['feat/' + t]) for t in num}
+    seeds = {'user': np.arange(num['user']), 'item': np.arange(num['item'])}
+    y = O.get_embeddings_full(num, [blk] * (meta['n_layers'] - 1), feats, state_dict(z), meta['out'], seeds,
+                              meta['aggregator'])
+    for t in num:
+        np.testing.assert_allclose(y[t].numpy(), z['emb/' + t], rtol=1e-4, atol=1e-5)
+    assert float(np.abs(z['emb/sport']).max()) == 0.0
