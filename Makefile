@@ -10,7 +10,9 @@ LIB       := $(PKG)/libgnn_recsys_b200.so
 
 all: $(LIB)
 
-build/%.o: $(PKG)/csrc/%.cu $(PKG)/csrc/common.cuh include/gnn_recsys_b200.h
+HDRS      := $(wildcard $(PKG)/csrc/*.cuh) include/gnn_recsys_b200.h
+
+build/%.o: $(PKG)/csrc/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: full-graph embeddings + top-10 recommendations for every user.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c5|c4]
 
 One "step" = one pass of the hot path over the whole synthetic graph: NodeEmbedding -> ConvLayer stack over the
 four relations -> all-users x all-items cosine + top-10. Rank 0 prints ONE JSON line (see the keys at the bottom).
@@ -38,7 +38,12 @@ WORKLOADS = {  # BASELINE.json configs: users, items, edges, n_layers, aggregato
     'c2': (1_000_000, 200_000, 50_000_000, 2, 'mean', 128, 128),
     'c3': (5_000_000, 500_000, 200_000_000, 3, 'pool_nn', 256, 128),
     'c5': (10_000_000, 1_000_000, 500_000_000, 2, 'mean', 128, 128),
+    # training-step forward (BASELINE configs[3]) on the c1 graph: fan-out [10, 10] blocks, 1024 positive edges + K
+    # uniform negatives each, CosinePrediction + max-margin loss. A side measurement (its own metric), not the bench line.
+    'c4': (10_000, 5_000, 200_000, 3, 'mean', 128, 128),
 }
+C4_BATCH, C4_FANOUTS, C4_DELTA = 1024, [10, 10], 0.266
+REV_ETYPES = {'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by', 'clicked-by': 'clicks'}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
@@ -181,6 +186,163 @@ def workload_config(name, wl, n_gpus, item_shards=None):
             'l2': 'inputs larger than L2 (CSR + tables >> 126 MB per step), no explicit flush'}
 
 
+
+# ------------------------------------------------------------------------------------------------ config 4
+def c4_oracle_step(g, batch, sd, neg_k):
+    """One training-step forward on the CPU oracle (reference semantics, torch CPU) for a host-built batch."""
+    from oracle import straightline as O
+    _, pos_g, neg_g, blocks = batch
+    obs = []
+    for b in blocks:
+        rels = {}
+        for c, r in b.rels.items():
+            dst = np.repeat(np.arange(r.n_dst), np.diff(r.indptr.numpy()))
+            rels[c] = (r.indices.numpy().astype(np.int64), dst, None)
+        obs.append(O.block_from_coo(b.num_src, b.num_dst, rels))
+    feats = {t: v for t, v in blocks[0].srcdata['features'].items()}
+    pe = {c: pos_g.edge_arrays(c) for c in pos_g.canonical_etypes}
+    ne = {c: neg_g.edge_arrays(c) for c in neg_g.canonical_etypes}
+    t0 = time.perf_counter()
+    h, pos, neg = O.model_forward(obs, feats, pe, ne, sd)
+    loss = O.max_margin_loss(pos, neg, C4_DELTA, neg_k)
+    return time.perf_counter() - t0, float(loss)
+
+
+def run_c4(args, wl):
+    """BASELINE configs[3]: EdgeDataLoader blocks (fan-out [10, 10]) + ConvModel.forward + max_margin_loss.
+    `value`: blocks built ON THE DEVICE (device= loader), CUDA events. `e2e`: the reference's call shape -- host loader,
+    block.to(device), forward, loss.item(). cpu_baseline / --impl reference: the oracle on the host cores."""
+    import gnn_recsys_b200 as grb
+    n_users, n_items, n_edges, n_layers, agg, hidden, out = wl
+    k = args.neg_k
+    data = grb.make_graph(n_users, n_items, n_edges, 0)
+    g = data.graph()
+    eids = {'buys': np.arange(g.num_edges('buys')), 'clicks': np.arange(g.num_edges('clicks'))}
+    kw = dict(exclude='reverse_types', reverse_etypes=REV_ETYPES, negative_sampler=grb.negative_sampler.Uniform(k),
+              batch_size=C4_BATCH, shuffle=True, seed=2)
+    workload = ('c4: training-step forward on %d users x %d items x %d edges: EdgeDataLoader fan-out %s, %d positive + %d x %d '
+                'negative edges, %d-layer ConvModel %s %d/%d, CosinePrediction + max-margin loss'
+                % (n_users, n_items, n_edges, C4_FANOUTS, C4_BATCH, C4_BATCH, k, n_layers, agg, hidden, out))
+    metric = 'training-step forwards/sec (sampled blocks + positive/negative cosine scores + loss)'
+    torch.manual_seed(1)
+    if args.impl == 'reference':
+        if int(os.environ.get('RANK', '0')) != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        stub = grb.ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, agg)
+        sd = {kk: v.detach() for kk, v in stub.state_dict().items()}
+        it = iter(grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler(C4_FANOUTS), **kw))
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            batch = next(it)
+            c4_oracle_step(g, batch, sd, k)
+            if i >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        v = 1.0 / float(np.mean(ts))
+        cores = torch.get_num_threads()
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'steps/s', 'n_gpus': args.gpus,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / v, 'higher_is_better': True,
+                          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': workload},
+                          'cpu_baseline': {'value': v, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+                                           'sample': 'host block builder + oracle model_forward + loss, %d steps' % args.steps},
+                          'e2e': {'value': v, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                          'gpu_launches': 0}))
+        return
+    N = grb._native
+    N.load()
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    model = grb.ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, agg).to(dev).eval()
+    pk = peaks()
+    g.full_block_on(dev)
+    dev_loader = grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler(C4_FANOUTS), device=dev, **kw)
+    host_loader = grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler(C4_FANOUTS), **kw)
+    neg_ev = []
+
+    def forward(batch, record=False):
+        _, pos_g, neg_g, blocks = batch
+        blocks = [b.to(dev) for b in blocks]
+        h = {t: v.to(dev, torch.float32, non_blocking=True) for t, v in blocks[0].srcdata['features'].items()}
+        h = model.get_repr(blocks, model.embed(h))
+        pos = model.pred_fn(pos_g, h)
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        neg = model.pred_fn(neg_g, h)
+        if record:
+            e1.record()
+            neg_ev.append((e0, e1, sum(int(v.shape[0]) for v in neg.values())))
+        return grb.max_margin_loss(pos, neg, C4_DELTA, k, cuda=True, device=dev)
+
+    sampler = ClockSampler(dev.index or 0)
+    it = iter(dev_loader)
+    for _ in range(max(args.warmup, 3)):
+        loss = forward(next(it))
+    torch.cuda.synchronize()
+    launches0 = N.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = forward(next(it), record=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    launches = N.kernel_launches() - launches0
+    clocks = sampler.stop(w0, w1)
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    # forward alone on a resident batch (what remains once block building is off the critical path)
+    batch = next(it)
+    for _ in range(3):
+        forward(batch)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        forward(batch)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_fwd = ev0.elapsed_time(ev1) / args.steps
+    # reference call shape: host loader -> .to(device) -> forward -> loss.item()
+    hit = iter(host_loader)
+    for _ in range(2):
+        float(forward(next(hit)))
+    h2d = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b = next(hit)
+        h2d += sum(r.csr_bytes() for blk in b[3] for r in blk.rels.values())
+        h2d += sum(int(v.numel()) * 4 for v in b[3][0].srcdata['features'].values())
+        h2d += sum(16 * gph.num_edges(c) for gph in (b[1], b[2]) for c in gph.canonical_etypes)
+        float(forward(b))
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    # edge-scoring kernel roofline: 8*D + 12 algorithmic bytes per edge (DESIGN.md 4.3)
+    ms_neg = float(np.mean([a.elapsed_time(b) for a, b, _ in neg_ev]))
+    n_neg = int(np.mean([n for _, _, n in neg_ev]))
+    gbs = n_neg * (8 * out + 12) / (ms_neg * 1e-3) / 1e9
+    roof = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm'], 'traffic': None,
+            'kernel': 'edge_cosine_kernel over the negative edges (both etypes, 2 launches)', 'of': pk['source'],
+            'note': 'gathers hit L2: the batch embedding tables are a few MB; algorithmic bytes = (8*D + 12) per edge'}
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = {kk: v.detach().cpu() for kk, v in model.state_dict().items()}
+        hb = next(iter(grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler(C4_FANOUTS), **kw)))
+        ts = [c4_oracle_step(g, hb, sd, k)[0] for _ in range(3)]
+        cpu = {'value': 1.0 / min(ts), 'unit': 'steps/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': 'oracle model_forward + loss on one host-built batch (blocks given), best of 3'}
+    print(json.dumps({
+        'metric': metric, 'value': 1e3 / ms_step, 'unit': 'steps/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': workload, 'l2': 'working set of a batch fits L2; no flush (latency-bound step)'},
+        'e2e': {'value': 1.0 / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d // args.steps, 'd2h_bytes_per_step': 4,
+                'ms_per_step': e2e_s * 1e3, 'note': 'host (NumPy) block builder + block.to(device) + forward + loss.item()'},
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        'stages_ms': {'device_blocks_plus_forward_ms': ms_step, 'forward_only_ms': ms_fwd, 'negative_scoring_ms': ms_neg},
+        'scored_edges_per_step': C4_BATCH * (1 + k), 'loss': float(loss)}))
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -193,11 +355,14 @@ def main():
     ap.add_argument('--parts', type=int, default=2, choices=[1, 2])
     ap.add_argument('--shortlist', type=int, default=16)
     ap.add_argument('--item-shards', type=int, default=None, help='N>1 scoring layout: N = item-range shards + owner-side top-k merge; 1 = user-range shards, replicated item table; default: shard the longer side')
+    ap.add_argument('--neg-k', type=int, default=2500, help='c4: negatives per positive edge (reference default 2500)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.config]
+    if args.config == 'c4':
+        return run_c4(args, wl)
     if args.impl == 'reference':
         return run_reference_arm(args, args.config, wl)
 

@@ -2,10 +2,11 @@
 
 Import as ``gnn_recsys_b200`` (the repo-root alias module) -- the directory name carries a hyphen.
 """
-from .graph import HeteroGraph, Block, Relation, heterograph, edge_graph, csr_by_dst_host, NID, EID  # noqa: F401
+from .graph import (HeteroGraph, Block, Relation, DeviceEdgeGraph, heterograph, edge_graph, csr_by_dst_host,  # noqa: F401
+                    NID, EID)
 from .synthetic import make_graph, make_graph_device, SyntheticData, CONFIGS  # noqa: F401
 from .dataloading import (MultiLayerFullNeighborSampler, MultiLayerNeighborSampler, NodeDataLoader,  # noqa: F401
-                          EdgeDataLoader, negative_sampler, to_block)
+                          EdgeDataLoader, negative_sampler, to_block, sample_key, hash64)
 from .model import (ConvModel, ConvLayer, NodeEmbedding, HeteroGraphConv, CosinePrediction,  # noqa: F401
                     max_margin_loss)
 from .train.run import get_embeddings  # noqa: F401

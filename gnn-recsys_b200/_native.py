@@ -56,6 +56,10 @@ SIGNATURES = {
     'gr_csr_build_i32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gr_remap_workspace_bytes': (_sz, [_i64]),
     'gr_remap_first_appearance_i64': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gr_sample_key': (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    'gr_sample_count_i32': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    'gr_sample_fill_i32': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, C.c_uint64, _vp, _vp, _vp, _vp]),
+    'gr_negative_uniform_i64': (C.c_int, [_vp, _vp, _i64, _i32, _i64, C.c_uint64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace {
 
@@ -60,54 +61,6 @@ __global__ void flag_first_kernel(const long long* __restrict__ raw, long long n
     first[i] = f;
     flag[i] = f == (int)i ? 1 : 0;
   }
-}
-
-// exclusive scan of `count` ints in place by ONE block (ingest-time only; ~40 ms at 500M elements)
-__global__ void __launch_bounds__(1024) scan1_kernel(int* __restrict__ data, long long count, int* __restrict__ total) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  constexpr int PER = 4;
-  for (long long base = 0; base < count; base += 1024 * PER) {
-    int v[PER];
-    int sum = 0;
-    const long long j0 = base + (long long)threadIdx.x * PER;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      v[i] = j0 + i < count ? data[j0 + i] : 0;
-      sum += v[i];
-    }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(gr::FULL, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      int ws = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(gr::FULL, ws, o);
-        if (lane >= o) ws += t;
-      }
-      s_warp[lane] = ws;
-    }
-    __syncthreads();
-    int run = s_carry + (w > 0 ? s_warp[w - 1] : 0) + incl - sum;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      if (j0 + i < count) data[j0 + i] = run;
-      run += v[i];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = run;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = s_carry;
 }
 
 __global__ void assign_kernel(const long long* __restrict__ raw, long long n, const int* __restrict__ first,
@@ -167,7 +120,7 @@ extern "C" int gr_remap_first_appearance_i64(const int64_t* raw, int64_t n, int3
   GR_LAUNCH_CHECK();
   flag_first_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, keys, vals, mask, first, rank);
   GR_LAUNCH_CHECK();
-  scan1_kernel<<<1, 1024, 0, st>>>(rank, n, n_unique);
+  gr::scan1_kernel<<<1, 1024, 0, st>>>(rank, n, n_unique);
   GR_LAUNCH_CHECK();
   assign_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, first, rank, new_ids,
                                       reinterpret_cast<long long*>(uniq_raw_or_null));

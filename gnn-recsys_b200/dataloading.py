@@ -2,15 +2,23 @@
 
 Mirrors the ``dgl.dataloading`` surface the reference uses (``main_inference.py:126-138``,
 ``src/sampling.py:153-241``): ``MultiLayerFullNeighborSampler``, ``MultiLayerNeighborSampler``,
-``NodeDataLoader``, ``EdgeDataLoader`` and ``negative_sampler.Uniform``. Sampling itself is outside the
-accelerated path; these classes exist so the reference's call sites keep working
-and so that config 4 (fan-out [10, 10] blocks + 1024 positive / 1024*K negative edges) has inputs.
+``NodeDataLoader``, ``EdgeDataLoader`` and ``negative_sampler.Uniform``, so that the reference's call sites keep
+working and config 4 (fan-out [10, 10] blocks + 1024 positive / 1024*K negative edges) has inputs.
+
+Two builders behind the same classes:
+  * the host builder in this file (NumPy) -- the reference's call shape: CPU loader, then ``block.to(device)``;
+  * ``device=`` on a loader: frontiers, negatives and ``to_block`` compaction run as CUDA kernels on the graph
+    structure resident in HBM (``sampling_device.py``; ``gr_sample_*``, ``gr_negative_uniform_i64``,
+    ``gr_remap_first_appearance_i64``) and the batch never touches the host.
+Both draw ONE 63-bit key per batch from the loader's generator; everything else is counter based
+(``hash64(key, edge id)``, see include/gnn_recsys_b200.h), so the two builders produce the same blocks bit for bit.
 
 Block layout follows DGL's ``to_block``: destination nodes = seeds in the given order; source nodes =
 the destination nodes first, then unseen edge sources in first-appearance order (canonical etype
-order, then edge-id order). ``NodeDataLoader(..., batch_size=None)`` -- the fast path -- yields a single
-full-graph block per layer instead of ``ceil(n/128)`` sampled mini-batches; for a full-neighbour
-sampler the embeddings of the seed nodes are identical.
+order, then destination row, then edge id -- the order of the block's CSR). ``NodeDataLoader(...,
+batch_size=None)`` -- the fast path -- yields a single full-graph block per layer instead of ``ceil(n/128)``
+sampled mini-batches; for a full-neighbour sampler the embeddings of the seed nodes are identical (SURVEY.md 8a,
+row a12).
 """
 from __future__ import annotations
 
@@ -39,6 +47,42 @@ def _relabel(ids: np.ndarray, space: np.ndarray) -> np.ndarray:
     return order[pos].astype(np.int64)
 
 
+_M64 = (1 << 64) - 1
+_GOLDEN = 0x9E3779B97F4A7C15
+
+
+def _fin64(x: int) -> int:
+    x ^= x >> 30
+    x = (x * 0xbf58476d1ce4e5b9) & _M64
+    x ^= x >> 27
+    x = (x * 0x94d049bb133111eb) & _M64
+    return x ^ (x >> 31)
+
+
+def sample_key(seed: int, stream_id: int) -> int:
+    """``gr_sample_key``: the 64-bit key of one random stream (layer x relation, or negatives of one etype)."""
+    return _fin64((_fin64((int(seed) + _GOLDEN) & _M64) + (int(stream_id) + 1) * _GOLDEN) & _M64)
+
+
+def hash64(key: int, ctr: np.ndarray) -> np.ndarray:
+    """Vectorised ``hash64(key, ctr)`` of include/gnn_recsys_b200.h (uint64 wrap-around arithmetic)."""
+    with np.errstate(over='ignore'):
+        x = (np.asarray(ctr).astype(np.uint64) + np.uint64(1)) * np.uint64(_GOLDEN) + np.uint64(key)
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xbf58476d1ce4e5b9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94d049bb133111eb)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+NEGATIVE_STREAM = 4096  # stream ids: layer * 64 + relation index for frontiers, NEGATIVE_STREAM + relation index
+
+
+def _draw_key(rng) -> int:
+    return int(rng.integers(0, 2 ** 63, dtype=np.int64))
+
+
 class _FrontierSampler:
     """Shared block builder; subclasses choose which in-edges of the seeds form the frontier."""
 
@@ -48,10 +92,10 @@ class _FrontierSampler:
     def _pick(self, layer: int, n_slots_per_row: np.ndarray, rng) -> Optional[np.ndarray]:
         return None  # None = keep every slot (full neighbourhood)
 
-    def frontier(self, g: HeteroGraph, seeds: Dict[str, np.ndarray], layer: int, rng, exclude=None):
+    def frontier(self, g: HeteroGraph, seeds: Dict[str, np.ndarray], layer: int, key: int, exclude=None):
         """Per canonical etype: (src ids, dst ids, edge ids) of the chosen in-edges, edge-id order."""
         out = {}
-        for c in g.canonical_etypes:
+        for ci, c in enumerate(g.canonical_etypes):
             s, d = g.edge_arrays(c)
             sd = seeds.get(c[2])
             if sd is None or sd.size == 0 or s.size == 0:
@@ -71,8 +115,8 @@ class _FrontierSampler:
             fan = self._fanout(layer)
             if fan is not None and eids.size:
                 row_of = np.repeat(np.arange(rows.size), deg)
-                key = rng.random(eids.size)
-                order = np.lexsort((key, row_of))
+                ticket = hash64(sample_key(key, layer * 64 + ci), eids) >> np.uint64(32)
+                order = np.lexsort((eids, ticket, row_of))  # in a row edge-id order == CSR-slot order
                 start = np.cumsum(deg) - deg
                 rank = np.arange(eids.size) - np.repeat(start, deg)
                 eids = eids[order][rank < fan]
@@ -83,13 +127,22 @@ class _FrontierSampler:
     def _fanout(self, layer: int):
         return None
 
-    def sample_blocks(self, g: HeteroGraph, seed_nodes: Dict[str, np.ndarray], rng=None, exclude=None,
-                      edge_weight: Optional[str] = None) -> List[Block]:
-        rng = rng if rng is not None else np.random.default_rng(0)
+    def sample_blocks(self, g: HeteroGraph, seed_nodes, rng=None, exclude=None, edge_weight: Optional[str] = None,
+                      key: Optional[int] = None, device=None) -> List[Block]:
+        """Blocks for ``seed_nodes``, innermost layer first. ``key`` (or one draw from ``rng``) fixes every random
+        choice; ``device`` = a CUDA device builds the blocks there (``seed_nodes`` / ``exclude`` may then be device
+        tensors) with the same result."""
+        if key is None:
+            key = _draw_key(rng if rng is not None else np.random.default_rng(0))
+        if device is not None and torch.device(device).type == 'cuda':
+            from .sampling_device import sample_blocks_device
+            return sample_blocks_device(g, self, seed_nodes, key, torch.device(device), exclude, edge_weight)
         seeds = {t: _as_np_ids(v).astype(np.int64) for t, v in seed_nodes.items()}
+        if exclude is not None:
+            exclude = {c: _as_np_ids(v).astype(np.int64) for c, v in exclude.items()}
         blocks: List[Block] = []
         for layer in reversed(range(self.num_layers)):
-            fr = self.frontier(g, seeds, layer, rng, exclude)
+            fr = self.frontier(g, seeds, layer, key, exclude)
             blocks.insert(0, to_block(g, fr, seeds, edge_weight))
             seeds = {t: blocks[0].srcnodes[t].data[NID].numpy() for t in blocks[0].srctypes}
         return blocks
@@ -97,16 +150,22 @@ class _FrontierSampler:
 
 def to_block(g: HeteroGraph, frontier, dst_nodes: Dict[str, np.ndarray], edge_weight: Optional[str] = None) -> Block:
     """Compact a frontier into a ``Block`` (DGL ``to_block`` semantics, see module docstring)."""
+    csr = {}
+    for c, (s, d, eids) in frontier.items():  # CSR order of every relation: destination row, then edge id
+        dn = dst_nodes.get(c[2], np.zeros(0, np.int64))
+        ld = _relabel(d, dn)
+        order = np.argsort(ld, kind='stable')
+        csr[c] = (s[order], ld, order)
     src_ids = {}
     for t in g.ntypes:
         parts = [dst_nodes[t]] if t in dst_nodes else []
-        parts += [fr[0] for c, fr in frontier.items() if c[0] == t]
+        parts += [csr[c][0] for c in frontier if c[0] == t]
         src_ids[t] = _first_appearance_unique(parts)
     rels = {}
     for c, (s, d, eids) in frontier.items():
         dn = dst_nodes.get(c[2], np.zeros(0, np.int64))
-        ls, ld = _relabel(s, src_ids[c[0]]), _relabel(d, dn)
-        order = np.argsort(ld, kind='stable')
+        ld, order = csr[c][1], csr[c][2]
+        ls = _relabel(s, src_ids[c[0]])
         indptr = np.zeros(dn.size + 1, dtype=np.int64)
         np.cumsum(np.bincount(ld, minlength=dn.size), out=indptr[1:])
         w = None
@@ -157,8 +216,9 @@ class NodeDataLoader:
     """
 
     def __init__(self, g: HeteroGraph, nids, block_sampler, batch_size=None, shuffle=False, drop_last=False,
-                 num_workers=0, seed=0, edge_weight=None, force_minibatch=False, **kwargs):
+                 num_workers=0, seed=0, edge_weight=None, force_minibatch=False, device=None, **kwargs):
         self.g, self.sampler = g, block_sampler
+        self.device = device
         self.nids = {t: _as_np_ids(v).astype(np.int64) for t, v in nids.items()}
         self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
         self.rng = np.random.default_rng(seed)
@@ -196,7 +256,8 @@ class NodeDataLoader:
                 ids = self._flat_i[sel[self._flat_t[sel] == ti]]
                 if ids.size:
                     seeds[t] = ids
-            blocks = self.sampler.sample_blocks(self.g, seeds, self.rng, edge_weight=self.edge_weight)
+            blocks = self.sampler.sample_blocks(self.g, seeds, edge_weight=self.edge_weight, key=_draw_key(self.rng),
+                                                device=self.device)
             yield ({t: blocks[0].srcnodes[t].data[NID] for t in blocks[0].srctypes},
                    {t: blocks[-1].dstnodes[t].data[NID] for t in blocks[-1].dsttypes}, blocks)
 
@@ -208,13 +269,20 @@ class _Uniform:
     def __init__(self, k):
         self.k = k
 
-    def __call__(self, g: HeteroGraph, eids_dict, rng):
+    def __call__(self, g: HeteroGraph, eids_dict, key):
+        """``key``: the batch key (int) or a NumPy generator to draw one from. Destination of negative j of edge e:
+        ``hash64(stream key, e * k + j) mod num_nodes`` -- the rule ``gr_negative_uniform_i64`` implements."""
+        key = key if isinstance(key, int) else _draw_key(key)
+        cets = g.canonical_etypes
         out = {}
         for c, eids in eids_dict.items():
             c = g.to_canonical_etype(c)
             s, _ = g.edge_arrays(c)
-            src = np.repeat(s[_as_np_ids(eids).astype(np.int64)].astype(np.int64), self.k)
-            out[c] = (src, rng.integers(0, g.num_nodes(c[2]), size=src.size, dtype=np.int64))
+            e = _as_np_ids(eids).astype(np.int64)
+            src = np.repeat(s[e].astype(np.int64), self.k)
+            ctr = (np.repeat(e, self.k) * self.k + np.tile(np.arange(self.k, dtype=np.int64), e.size)).astype(np.uint64)
+            dst = hash64(sample_key(key, NEGATIVE_STREAM + cets.index(c)), ctr) % np.uint64(g.num_nodes(c[2]))
+            out[c] = (src, dst.astype(np.int64))
         return out
 
 
@@ -231,7 +299,8 @@ class EdgeDataLoader:
 
     def __init__(self, g: HeteroGraph, eids, block_sampler, g_sampling=None, exclude=None, reverse_etypes=None,
                  negative_sampler=None, batch_size=1, shuffle=False, drop_last=False, num_workers=0, seed=0,
-                 pin_memory=False, **kwargs):
+                 pin_memory=False, device=None, **kwargs):
+        self.device = device
         self.g, self.g_sampling = g, (g_sampling if g_sampling is not None else g)
         self.sampler, self.neg = block_sampler, negative_sampler
         self.exclude, self.reverse_etypes = exclude, reverse_etypes or {}
@@ -254,9 +323,14 @@ class EdgeDataLoader:
             sel = order[b * self.batch_size:(b + 1) * self.batch_size]
             items = {c: self._flat_e[sel[self._flat_t[sel] == i]] for i, c in enumerate(self._types)}
             items = {c: e for c, e in items.items() if e.size}
+            key = _draw_key(self.rng)
+            if self.device is not None and torch.device(self.device).type == 'cuda':
+                from .sampling_device import edge_batch_device
+                yield edge_batch_device(self, items, key, torch.device(self.device))
+                continue
             pos = {c: (g.edge_arrays(c)[0][e].astype(np.int64), g.edge_arrays(c)[1][e].astype(np.int64))
                    for c, e in items.items()}
-            neg = self.neg(g, items, self.rng) if self.neg is not None else {}
+            neg = self.neg(g, items, key) if self.neg is not None else {}
             space = {}
             for t in g.ntypes:
                 parts = []
@@ -291,5 +365,5 @@ class EdgeDataLoader:
                     rc = g.to_canonical_etype(self.reverse_etypes[c[1]])
                     exclude[rc] = np.concatenate([exclude.get(rc, np.zeros(0, np.int64)), e])
             seeds = {t: v for t, v in space.items() if v.size}
-            blocks = self.sampler.sample_blocks(self.g_sampling, seeds, self.rng, exclude)
+            blocks = self.sampler.sample_blocks(self.g_sampling, seeds, exclude=exclude, key=key)
             yield ({t: blocks[0].srcnodes[t].data[NID] for t in blocks[0].srctypes}, pos_g, neg_g, blocks)

@@ -242,6 +242,7 @@ class HeteroGraph:
         self._csr_cache: Dict[CEType, Tuple[np.ndarray, np.ndarray, np.ndarray]] = {}
         self._dev_blocks: Dict = {}
         self._dev_edges: Dict = {}
+        self._dev_node_data: Dict = {}
 
     # ---- metagraph ----
     @property
@@ -388,6 +389,19 @@ class HeteroGraph:
                                     torch.from_numpy(d.astype(np.int32)).to(device))
         return self._dev_edges[key]
 
+    def device_node_data(self, ntype, device) -> Dict[str, torch.Tensor]:
+        """Node frame of one type as device tensors (cached per host tensor) -- device-built blocks gather their
+        ``srcdata`` / ``dstdata`` rows from it instead of re-sending features with every batch."""
+        out = {}
+        for k, v in self._node_frames[ntype].items():
+            key = (ntype, str(device), k)
+            hit = self._dev_node_data.get(key)
+            if hit is None or hit[0] is not v or hit[1] != v._version:
+                hit = (v, v._version, v.to(device))
+                self._dev_node_data[key] = hit
+            out[k] = hit[2]
+        return out
+
     def to(self, device, **kwargs):
         return self  # structure stays on the host; blocks carry the device-resident CSR
 
@@ -400,3 +414,69 @@ def heterograph(data_dict, num_nodes_dict=None) -> HeteroGraph:
 def edge_graph(parent_ntype_sizes: Dict[str, int], edges: Dict[CEType, Tuple]) -> HeteroGraph:
     """Graph holding only edges to be scored (the ``pos_g`` / ``neg_g`` of ``src/model.py:423-470``)."""
     return HeteroGraph(edges, parent_ntype_sizes)
+
+
+class DeviceEdgeGraph:
+    """Edges to be scored, already on the device: the ``pos_g`` / ``neg_g`` a device-side ``EdgeDataLoader`` yields
+    (``src/train/run.py:104-116``). Node ids are local to the batch's seed space (= destination nodes of
+    ``blocks[-1]``); ``nodes[nt].data[NID]`` holds the global ids, ``edges[c].data[EID]`` the parent edge ids."""
+    is_block = False
+
+    def __init__(self, edges: Dict[CEType, Tuple[torch.Tensor, torch.Tensor]], num_nodes: Dict[str, int],
+                 node_ids: Optional[Dict[str, torch.Tensor]] = None, edge_ids: Optional[Dict] = None):
+        self._edges = dict(sorted(edges.items()))
+        self._num = dict(sorted(num_nodes.items()))
+        self._node_frames = {t: ({NID: node_ids[t]} if node_ids and t in node_ids else {}) for t in self._num}
+        self._edge_frames = {c: ({EID: edge_ids[c]} if edge_ids and c in edge_ids else {}) for c in self._edges}
+
+    @property
+    def ntypes(self):
+        return list(self._num.keys())
+
+    @property
+    def canonical_etypes(self):
+        return list(self._edges.keys())
+
+    @property
+    def etypes(self):
+        return [c[1] for c in self._edges]
+
+    to_canonical_etype = HeteroGraph.to_canonical_etype
+
+    def num_nodes(self, ntype=None):
+        return sum(self._num.values()) if ntype is None else self._num[ntype]
+
+    number_of_nodes = num_nodes
+
+    def num_edges(self, etype=None):
+        if etype is None:
+            return sum(int(e[0].shape[0]) for e in self._edges.values())
+        return int(self._edges[self.to_canonical_etype(etype)][0].shape[0])
+
+    number_of_edges = num_edges
+
+    @property
+    def nodes(self):
+        return _TypedIndex(self._node_frames)
+
+    @property
+    def edges(self):
+        return _TypedIndex(self._edge_frames, self.to_canonical_etype)
+
+    def device_edges(self, etype, device):
+        u, v = self._edges[self.to_canonical_etype(etype)]
+        if u.device != torch.device(device):
+            u, v = u.to(device), v.to(device)
+        return u, v
+
+    def edge_arrays(self, etype):
+        """Host copies (int64 numpy) -- for inspection and tests; the scoring kernel reads ``device_edges``."""
+        u, v = self._edges[self.to_canonical_etype(etype)]
+        return u.cpu().numpy().astype(np.int64), v.cpu().numpy().astype(np.int64)
+
+    def all_edges(self, form='uv', order=None, etype=None):
+        u, v = self._edges[self.to_canonical_etype(etype)]
+        return u.long(), v.long()
+
+    def to(self, device, **kwargs):
+        return self

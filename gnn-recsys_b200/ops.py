@@ -208,3 +208,41 @@ def remap_first_appearance(raw: torch.Tensor):
     N.call('gr_remap_first_appearance_i64', N.ptr(raw), n, N.ptr(new_ids), N.ptr(uniq), N.ptr(n_unique), N.ptr(ws),
            ws.numel(), N.stream())
     return new_ids, uniq[:int(n_unique.item())]
+
+
+def sample_count(indptr: torch.Tensor, eperm: Optional[torch.Tensor], seeds: torch.Tensor, fanout: int,
+                 excl_sorted: Optional[torch.Tensor] = None):
+    """Per-seed frontier sizes of one relation as the block's ``indptr`` (int32 ``[n_seeds + 1]``) plus the device
+    scalar ``total`` (see include/gnn_recsys_b200.h, ``gr_sample_count_i32``)."""
+    assert seeds.dtype == torch.int64 and indptr.dtype == torch.int32
+    n = int(seeds.shape[0])
+    dev = indptr.device
+    out_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    n_excl = 0 if excl_sorted is None else int(excl_sorted.shape[0])
+    N.call('gr_sample_count_i32', N.ptr(indptr), N.ptr(eperm) if eperm is not None else None, N.ptr(seeds), n,
+           int(fanout), N.ptr(excl_sorted) if n_excl else None, n_excl, N.ptr(out_indptr), N.ptr(total), N.stream())
+    return out_indptr, total
+
+
+def sample_fill(indptr, indices, eperm, seeds, fanout: int, excl_sorted, key: int, out_indptr, out_src: torch.Tensor,
+                out_eid: torch.Tensor):
+    """Writes the frontier's global source ids (int64) and edge ids (int32) into ``out_src`` / ``out_eid`` (views are
+    fine: only their first ``total`` entries are written)."""
+    assert out_src.dtype == torch.int64 and out_eid.dtype == torch.int32
+    n_excl = 0 if excl_sorted is None else int(excl_sorted.shape[0])
+    N.call('gr_sample_fill_i32', N.ptr(indptr), N.ptr(indices), N.ptr(eperm) if eperm is not None else None,
+           N.ptr(seeds), int(seeds.shape[0]), int(fanout), N.ptr(excl_sorted) if n_excl else None, n_excl,
+           int(key) & 0xFFFFFFFFFFFFFFFF, N.ptr(out_indptr), N.ptr(out_src), N.ptr(out_eid), N.stream())
+
+
+def negative_uniform(edge_src: torch.Tensor, eids: torch.Tensor, k: int, n_dst_nodes: int, key: int):
+    """``negative_sampler.Uniform(k)`` on the device: ``(src, dst)`` int64 ``[n_pos * k]``, k consecutive per edge."""
+    assert edge_src.dtype == torch.int32 and eids.dtype == torch.int64
+    n = int(eids.shape[0])
+    dev = edge_src.device
+    src = torch.empty(n * k, dtype=torch.int64, device=dev)
+    dst = torch.empty(n * k, dtype=torch.int64, device=dev)
+    N.call('gr_negative_uniform_i64', N.ptr(edge_src), N.ptr(eids), n, int(k), int(n_dst_nodes),
+           int(key) & 0xFFFFFFFFFFFFFFFF, N.ptr(src), N.ptr(dst), N.stream())
+    return src, dst

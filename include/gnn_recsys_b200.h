@@ -171,6 +171,35 @@ size_t gr_remap_workspace_bytes(int64_t n);
 int gr_remap_first_appearance_i64(const int64_t* raw, int64_t n, int32_t* new_ids, int64_t* uniq_raw_or_null,
                                   int32_t* n_unique, void* ws, size_t ws_bytes, gr_stream_t stream);
 
+/* ---- sampled blocks next to the path: the frontier sampling and negative sampling that
+ *      dgl.dataloading does on the CPU behind the reference's EdgeDataLoader / NodeDataLoader (src/sampling.py:153-207;
+ *      consumed by the training-step forward, src/train/run.py:89-139). Counter-based randomness, restated bit for bit
+ *      by oracle.straightline.sample_frontier / negative_uniform:
+ *        hash64(key, ctr) = fin(key + (ctr + 1) * 0x9E3779B97F4A7C15), fin = the splitmix64 finaliser
+ *        gr_sample_key(seed, stream_id) = hash64(fin(seed + 0x9E3779B97F4A7C15), stream_id)   (host helper, no GPU)
+ *
+ *  gr_sample_count_i32 / gr_sample_fill_i32: frontier of one relation (CSR over destination rows as built by
+ *      gr_csr_build_i32; eperm NULL = edge id == CSR slot) for `seeds` (distinct destination ids, int64 like DGL's
+ *      NID). fanout <= 0: every in-edge (MultiLayerFullNeighborSampler / in_subgraph); 1..32: at most `fanout`
+ *      in-edges per seed, uniformly without replacement (MultiLayerNeighborSampler(fanouts, replace=False)): the
+ *      candidates with the smallest (hash64(key, edge id) >> 32, CSR slot). Edge ids in `excl_sorted` (ascending int32;
+ *      the batch's own edges and their reverse twins, exclude='reverse_types') are never candidates.
+ *      count: out_indptr[n_seeds + 1] = exclusive scan of the per-seed counts (the block's indptr), *total =
+ *      out_indptr[n_seeds] (device int32). fill: out_src[total] (GLOBAL source ids, int64 so that the buffer can feed
+ *      gr_remap_first_appearance_i64 directly) and out_eid[total], per seed in CSR (= edge id) order.
+ *  gr_negative_uniform_i64: negative_sampler.Uniform(k): for positive edge e (id eids[e], source edge_src[eids[e]]):
+ *      out_src[e*k + j] = that source, out_dst[e*k + j] = hash64(key, eids[e]*k + j) mod n_dst_nodes, j < k. */
+uint64_t gr_sample_key(uint64_t seed, uint64_t stream_id);
+int gr_sample_count_i32(const int32_t* indptr, const int32_t* eperm_or_null, const int64_t* seeds, int64_t n_seeds,
+                        int32_t fanout, const int32_t* excl_sorted_or_null, int32_t n_excl, int32_t* out_indptr,
+                        int32_t* total, gr_stream_t stream);
+int gr_sample_fill_i32(const int32_t* indptr, const int32_t* indices, const int32_t* eperm_or_null,
+                       const int64_t* seeds, int64_t n_seeds, int32_t fanout, const int32_t* excl_sorted_or_null,
+                       int32_t n_excl, uint64_t key, const int32_t* out_indptr, int64_t* out_src, int32_t* out_eid,
+                       gr_stream_t stream);
+int gr_negative_uniform_i64(const int32_t* edge_src, const int64_t* eids, int64_t n_pos, int32_t k,
+                            int64_t n_dst_nodes, uint64_t key, int64_t* out_src, int64_t* out_dst, gr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

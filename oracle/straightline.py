@@ -298,3 +298,84 @@ def merge_partial_topk(scores_list, ids_list, k):
     s = np.where(i < 0, -np.inf, s)
     order = np.argsort(-s, axis=1, kind='stable')[:, :k]
     return np.take_along_axis(s, order, 1), np.take_along_axis(i, order, 1)
+
+
+# ----------------------------------------------------------------------------------------------- sampled blocks
+# what dgl.dataloading does behind the reference's loaders (src/sampling.py:153-207):
+# MultiLayerNeighborSampler(fanouts, replace=False) / MultiLayerFullNeighborSampler frontiers, to_block compaction,
+# negative_sampler.Uniform(k). DGL's own random streams cannot be reproduced (library absent, see PARITY STATUS):
+# the SEMANTICS are restated (at most `fanout` distinct in-edges per seed and relation, drawn uniformly; seeds first
+# in the block's source space; k negatives per positive edge laid out consecutively, destination uniform over the
+# node type) on top of the product's counter-based randomness, restated here with plain Python integers.
+_M64 = (1 << 64) - 1
+_GOLDEN = 0x9E3779B97F4A7C15
+
+
+def _fin64(x):
+    x ^= x >> 30
+    x = (x * 0xbf58476d1ce4e5b9) & _M64
+    x ^= x >> 27
+    x = (x * 0x94d049bb133111eb) & _M64
+    x ^= x >> 31
+    return x
+
+
+def hash64(key, ctr):
+    return _fin64((key + (ctr + 1) * _GOLDEN) & _M64)
+
+
+def sample_key(seed, stream_id):
+    return hash64(_fin64((seed + _GOLDEN) & _M64), stream_id)
+
+
+def sample_frontier(indptr, indices, eperm, seeds, fanout, key, exclude=()):
+    """Frontier of one relation for ``seeds`` (distinct destination ids): per seed the in-edges that are not in
+    ``exclude``; with ``fanout`` >= 1 only the ``fanout`` of them with the smallest (hash64(key, eid) >> 32, CSR slot),
+    emitted in CSR (= edge id) order. Returns ``(out_indptr, src_global, eids)``."""
+    exclude = set(int(e) for e in exclude)
+    out_indptr, src, eids = [0], [], []
+    for row in seeds:
+        row = int(row)
+        cand = []
+        for slot in range(int(indptr[row]), int(indptr[row + 1])):
+            eid = int(eperm[slot]) if eperm is not None else slot
+            if eid not in exclude:
+                cand.append((hash64(key, eid) >> 32, slot - int(indptr[row]), eid, int(indices[slot])))
+        if fanout is not None and fanout > 0 and len(cand) > fanout:
+            cand = sorted(cand)[:fanout]
+        cand.sort(key=lambda c: c[1])
+        src += [c[3] for c in cand]
+        eids += [c[2] for c in cand]
+        out_indptr.append(len(src))
+    return np.asarray(out_indptr, np.int32), np.asarray(src, np.int64), np.asarray(eids, np.int32)
+
+
+def negative_uniform(edge_src, eids, k, n_dst_nodes, key):
+    """``negative_sampler.Uniform(k)``: (src of the positive edge, uniform destination), k consecutive per edge."""
+    src, dst = [], []
+    for eid in eids:
+        eid = int(eid)
+        for j in range(k):
+            src.append(int(edge_src[eid]))
+            dst.append(hash64(key, eid * k + j) % n_dst_nodes)
+    return np.asarray(src, np.int64), np.asarray(dst, np.int64)
+
+
+def compact_block(ntypes, canonical_etypes, seeds, frontiers):
+    """``to_block``: destination nodes = seeds in the given order; source nodes = the seeds first, then unseen frontier
+    sources in first-appearance order (canonical etype order, then CSR order). ``frontiers[c]`` is a
+    ``sample_frontier`` result. Returns ``(src_ids {nt: global ids}, rels {c: (indptr, local src, eids)})``."""
+    src_ids, local = {}, {}
+    for t in ntypes:
+        parts = [np.asarray(seeds[t], np.int64)] if t in seeds else []
+        parts += [frontiers[c][1] for c in canonical_etypes if c[0] == t and c in frontiers]
+        cat = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+        _, uniq = first_appearance_ids([int(v) for v in cat])
+        src_ids[t] = np.asarray(uniq, np.int64)
+        local[t] = {g: i for i, g in enumerate(uniq)}
+    rels = {}
+    for c in canonical_etypes:
+        if c in frontiers:
+            ip, s, e = frontiers[c]
+            rels[c] = (ip, np.asarray([local[c[0]][int(g)] for g in s], np.int32), e)
+    return src_ids, rels

@@ -5,6 +5,8 @@ import os
 import numpy as np
 import torch
 
+from oracle import straightline as O
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 RELS = [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]
@@ -47,3 +49,40 @@ def assert_topk_equivalent(got, want, scores, k, tol=1e-5):
         sg, sw = scores[r, got[r][valid]], scores[r, want[r][valid]]
         assert np.all(np.abs(sg - sw) < tol), 'row %d: ids differ beyond score ties: %s vs %s' % (r, got[r], want[r])
         assert len(set(got[r][valid].tolist())) == int(valid.sum()), 'row %d: duplicate ids' % r
+
+
+def oracle_blocks(g, sampler, seeds, key, exclude=None):
+    """Blocks restated by the oracle (sample_frontier + compact_block), innermost layer first."""
+    cets = g.canonical_etypes
+    seeds = {t: np.asarray(v, np.int64) for t, v in seeds.items() if len(v)}
+    out = []
+    for layer in reversed(range(sampler.num_layers)):
+        fr = {}
+        for ci, c in enumerate(cets):
+            if c[2] in seeds and g.num_edges(c):
+                indptr, indices, eperm = g.csr(c)
+                fr[c] = O.sample_frontier(indptr, indices, eperm, seeds[c[2]], sampler._fanout(layer),
+                                          O.sample_key(key, layer * 64 + ci), (exclude or {}).get(c, ()))
+        src_ids, rels = O.compact_block(g.ntypes, cets, seeds, fr)
+        out.insert(0, (src_ids, rels, dict(seeds)))
+        seeds = {t: v for t, v in src_ids.items() if v.size}
+    return out
+
+
+def assert_blocks_equal_oracle(blocks, want, g):
+    for b, (src_ids, rels, seeds) in zip(blocks, want):
+        for t in g.ntypes:
+            assert b.srcnodes[t].data['_ID'].cpu().tolist() == src_ids[t].tolist()
+            assert b.dstnodes[t].data['_ID'].cpu().tolist() == seeds.get(t, np.zeros(0)).tolist()
+            assert b.num_src[t] == src_ids[t].size and b.num_dst[t] == (seeds[t].size if t in seeds else 0)
+            for name, v in g.nodes[t].data.items():
+                assert torch.equal(b.srcnodes[t].data[name].cpu(), v[torch.from_numpy(src_ids[t])])
+        for c in g.canonical_etypes:
+            r = b.rels[c]
+            if c in rels:
+                ip, ls, e = rels[c]
+                assert r.indptr.cpu().tolist() == ip.tolist() and r.indices.cpu().tolist() == ls.tolist()
+                assert r.eperm.cpu().tolist() == e.tolist()
+            else:
+                assert r.nnz == 0 and r.indptr.cpu().tolist() == [0] * (r.n_dst + 1)
+            assert r.n_src == b.num_src[c[0]] and r.n_dst == b.num_dst[c[2]]

@@ -506,3 +506,157 @@ def test_duplicate_items_overflow_path_and_fp16_never_overflows(grb):
         assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
         if elem == 'fp16':
             assert int(n_over) == 0
+
+
+# ------------------------------------------------------------------------------------------------ sampled blocks on the device
+def _random_relation(rng, n_src, n_dst, nnz, hub=7, hub_edges=5000):
+    src = rng.integers(0, n_src, nnz)
+    dst = rng.integers(0, n_dst, nnz)
+    dst[dst == 3] = 4                      # row 3 has no in-edge
+    dst[rng.choice(nnz, hub_edges, replace=False)] = hub   # a hub row far above one warp pass
+    return src.astype(np.int64), dst.astype(np.int64)
+
+
+@pytest.mark.parametrize('with_eperm', [True, False])
+def test_sample_kernels_bit_exact_vs_oracle(grb, with_eperm):
+    dev = torch.device('cuda:0')
+    rng = np.random.default_rng(11)
+    n_src, n_dst, nnz = 500, 200, 20000
+    src, dst = _random_relation(rng, n_src, n_dst, nnz)
+    indptr, indices, eperm = grb.ops.csr_build(torch.from_numpy(src.astype(np.int32)).to(dev),
+                                               torch.from_numpy(dst.astype(np.int32)).to(dev), n_dst)
+    h_indptr, h_indices = indptr.cpu().numpy(), indices.cpu().numpy()
+    h_eperm = eperm.cpu().numpy() if with_eperm else None
+    seeds = np.concatenate([[7, 3], rng.permutation(np.setdiff1d(np.arange(n_dst), [7, 3]))[:90]]).astype(np.int64)
+    seeds_d = torch.from_numpy(seeds).to(dev)
+    excl = np.unique(rng.integers(0, nnz, 3000)).astype(np.int32)
+    for fan in (0, 1, 10, 32):
+        for ex in (None, excl):
+            key = grb.sample_key(1234 + fan, 3)
+            ex_d = torch.from_numpy(ex).to(dev) if ex is not None else None
+            out_indptr, total = grb.ops.sample_count(indptr, eperm if with_eperm else None, seeds_d, fan, ex_d)
+            n = int(total.item())
+            out_src = torch.full((n,), -1, dtype=torch.int64, device=dev)
+            out_eid = torch.full((n,), -1, dtype=torch.int32, device=dev)
+            if n:
+                grb.ops.sample_fill(indptr, indices, eperm if with_eperm else None, seeds_d, fan, ex_d, key, out_indptr,
+                                    out_src, out_eid)
+            w_indptr, w_src, w_eid = O.sample_frontier(h_indptr, h_indices, h_eperm, seeds, fan, key,
+                                                       ex if ex is not None else ())
+            assert out_indptr.cpu().tolist() == w_indptr.tolist() and n == int(w_indptr[-1])
+            assert out_src.cpu().tolist() == w_src.tolist()
+            assert out_eid.cpu().tolist() == w_eid.tolist()
+    # no seeds at all
+    out_indptr, total = grb.ops.sample_count(indptr, eperm, torch.zeros(0, dtype=torch.int64, device=dev), 10)
+    assert out_indptr.cpu().tolist() == [0] and int(total.item()) == 0
+    with pytest.raises(grb._native.NativeError):
+        grb.ops.sample_count(indptr, eperm, seeds_d, 33)
+
+
+def test_negative_uniform_bit_exact_vs_oracle(grb):
+    dev = torch.device('cuda:0')
+    rng = np.random.default_rng(3)
+    edge_src = rng.integers(0, 1000, 5000).astype(np.int32)
+    eids = rng.integers(0, 5000, 300).astype(np.int64)
+    for k, n_dst in ((1, 7), (20, 5000), (2500, 1_000_003)):
+        key = grb.sample_key(77, 4096 + k)
+        e = eids[:40] if k > 100 else eids
+        s, d = grb.ops.negative_uniform(torch.from_numpy(edge_src).to(dev), torch.from_numpy(e).to(dev), k, n_dst, key)
+        ws, wd = O.negative_uniform(edge_src, e, k, n_dst, key)
+        assert s.cpu().tolist() == ws.tolist() and d.cpu().tolist() == wd.tolist()
+    s, d = grb.ops.negative_uniform(torch.from_numpy(edge_src).to(dev), torch.zeros(0, dtype=torch.int64, device=dev), 5, 9, 1)
+    assert s.numel() == 0 and d.numel() == 0
+
+
+def _training_graph(grb, seed=0, occurrence=False):
+    d = grb.make_graph(300, 120, 5000, seed)
+    g = d.graph()
+    if occurrence:
+        rng = np.random.default_rng(seed)
+        for fwd, bwd in (('buys', 'bought-by'), ('clicks', 'clicked-by')):
+            occ = torch.from_numpy(rng.integers(1, 5, g.num_edges(fwd)).astype(np.float32))
+            g.edges[fwd].data['occurrence'], g.edges[bwd].data['occurrence'] = occ, occ
+    return d, g
+
+
+REV = {'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by', 'clicked-by': 'clicks'}
+
+
+@pytest.mark.parametrize('sampler_kind', ['fanout', 'full'])
+def test_device_edge_loader_matches_host_loader_and_oracle(grb, sampler_kind):
+    """BASELINE config 4 built entirely on the device == the host builder (bit for bit) == the oracle's restatement;
+    the training-step forward on either set of blocks gives the same scores and loss."""
+    from helpers import oracle_blocks, assert_blocks_equal_oracle
+    dev = torch.device('cuda:0')
+    d, g = _training_graph(grb)
+    eids = {'buys': np.arange(g.num_edges('buys')), 'clicks': np.arange(g.num_edges('clicks'))}
+    mk = (lambda: grb.MultiLayerNeighborSampler([10, 10])) if sampler_kind == 'fanout' else \
+        (lambda: grb.MultiLayerFullNeighborSampler(2))
+    kw = dict(exclude='reverse_types', reverse_etypes=REV, negative_sampler=grb.negative_sampler.Uniform(20),
+              batch_size=64, shuffle=True, seed=9)
+    host = grb.EdgeDataLoader(g, eids, mk(), **kw)
+    devl = grb.EdgeDataLoader(g, eids, mk(), device=dev, **kw)
+    torch.manual_seed(1)
+    model = grb.ConvModel(g, 3, {'user': 2, 'item': 4, 'hidden': 32, 'out': 16}, True, 0.0, 'mean', 'cos', 'sum', True)
+    model = model.to(dev).eval()
+    key_rng = np.random.default_rng(9)
+    n_batches = 0
+    for (in_h, pos_h, neg_h, blocks_h), (in_d, pos_d, neg_d, blocks_d) in zip(host, devl):
+        n_batches += 1
+        for c in g.canonical_etypes:
+            for a, b in ((pos_h, pos_d), (neg_h, neg_d)):
+                assert a.num_edges(c) == b.num_edges(c)
+                for x, y in zip(a.edge_arrays(c), b.edge_arrays(c)):
+                    assert x.tolist() == y.tolist()
+        for t in g.ntypes:
+            assert pos_h.nodes[t].data[grb.NID].tolist() == pos_d.nodes[t].data[grb.NID].cpu().tolist()
+            assert in_h[t].tolist() == in_d[t].cpu().tolist()
+        for bh, bd in zip(blocks_h, blocks_d):
+            assert bh.num_src == bd.num_src and bh.num_dst == bd.num_dst
+            for c in g.canonical_etypes:
+                rh, rd = bh.rels[c], bd.rels[c]
+                assert rd.indptr.is_cuda and rh.indptr.tolist() == rd.indptr.cpu().tolist()
+                assert rh.indices.tolist() == rd.indices.cpu().tolist()
+                assert rh.eperm.tolist() == rd.eperm.cpu().tolist()
+            for t in g.ntypes:
+                assert torch.equal(bh.srcnodes[t].data['features'], bd.srcnodes[t].data['features'].cpu())
+        if n_batches == 1:  # the oracle's restatement of the same batch (same key stream: permutation, then one key)
+            key_rng.permutation(sum(v.size for v in eids.values()))
+            key = int(key_rng.integers(0, 2 ** 63, dtype=np.int64))
+            seeds = {t: pos_d.nodes[t].data[grb.NID].cpu().numpy() for t in g.ntypes}
+            excl = {}
+            for c in (('user', 'buys', 'item'), ('user', 'clicks', 'item')):
+                e = pos_d.edges[c].data[grb.EID].cpu().numpy()
+                excl[c] = e
+                excl[g.to_canonical_etype(REV[c[1]])] = e
+            assert_blocks_equal_oracle(blocks_d, oracle_blocks(g, devl.sampler, seeds, key, excl), g)
+        h_d, ps_d, ns_d = model(blocks_d, dict(blocks_d[0].srcdata['features']), pos_d, neg_d, True)
+        h_h, ps_h, ns_h = model([b.to(dev) for b in blocks_h], dict(blocks_h[0].srcdata['features']), pos_h, neg_h, True)
+        for t in g.ntypes:
+            assert torch.equal(h_d[t], h_h[t])
+        for c in ps_d:
+            assert torch.equal(ps_d[c], ps_h[c]) and torch.equal(ns_d[c], ns_h[c])
+        loss = grb.max_margin_loss(ps_d, ns_d, 0.266, 20)
+        assert torch.isfinite(loss)
+        if n_batches == 3:
+            break
+    assert n_batches == 3
+
+
+def test_device_node_loader_minibatches_and_edge_weights(grb):
+    """NodeDataLoader(device=...) mini-batches (full-neighbour sampler) reproduce the one-pass embeddings, including
+    the per-edge 'occurrence' weights of the *_edge aggregators gathered on the device."""
+    dev = torch.device('cuda:0')
+    d, g = _training_graph(grb, seed=2, occurrence=True)
+    torch.manual_seed(3)
+    model = grb.ConvModel(g, 3, {'user': 2, 'item': 4, 'hidden': 16, 'out': 8}, True, 0.0, 'mean_edge', 'cos', 'sum', True)
+    model = model.to(dev).eval()
+    nids = {'user': np.arange(300), 'item': np.arange(120)}
+    one = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(2), batch_size=None, edge_weight='occurrence')
+    want = grb.get_embeddings(g, 8, model, one, 1, False, dev, True)
+    for device in (dev, None):
+        mini = grb.NodeDataLoader(g, nids, grb.MultiLayerFullNeighborSampler(2), batch_size=64, shuffle=True, seed=4,
+                                  edge_weight='occurrence', force_minibatch=True, device=device)
+        got = grb.get_embeddings(g, 8, model, mini, len(mini), False, dev, True)
+        for t in g.ntypes:
+            np.testing.assert_allclose(got[t].numpy(), want[t].numpy(), rtol=RTOL, atol=ATOL)

@@ -5,6 +5,7 @@ import torch
 
 import gnn_recsys_b200 as grb
 from oracle import straightline as O
+from helpers import oracle_blocks, assert_blocks_equal_oracle
 
 
 def small_graph(seed=0, n_edges=400):
@@ -160,3 +161,153 @@ def test_unsupported_options_fail_loudly():
     assert 'layers.0.mods.bought-by.fc_preagg.weight' in keys and 'layers.1.mods.clicks.fc_neigh.weight' in keys
     assert len(m.layers) == 2
     assert len(grb.ConvModel(g, 2, dims, embedding_layer=False).layers) == 2
+
+
+# ------------------------------------------------------------------------------------------------ sampled blocks
+def test_counter_based_hash_matches_oracle_and_library_key():
+    import ctypes as C
+    from gnn_recsys_b200 import _native as N
+    lib = C.CDLL(N.LIB_PATH)  # host-only entry point: no GPU needed
+    lib.gr_sample_key.restype, lib.gr_sample_key.argtypes = C.c_uint64, [C.c_uint64, C.c_uint64]
+    rng = np.random.default_rng(0)
+    for seed, stream in [(0, 0), (1, 5), (2 ** 63 - 1, 4099), (int(rng.integers(0, 2 ** 63)), 130)]:
+        k = grb.sample_key(seed, stream)
+        assert k == O.sample_key(seed, stream) == lib.gr_sample_key(seed, stream)
+        ctr = np.concatenate([np.arange(50), rng.integers(0, 2 ** 62, 50)]).astype(np.int64)
+        assert grb.hash64(k, ctr).tolist() == [O.hash64(k, int(c)) for c in ctr]
+
+
+@pytest.mark.parametrize('fanouts', [[3, 2], [1], None])
+def test_host_sampler_matchesoracle_blocks(fanouts):
+    d, g = small_graph(5, 900)
+    sampler = grb.MultiLayerNeighborSampler(fanouts) if fanouts else grb.MultiLayerFullNeighborSampler(2)
+    seeds = {'user': np.array([7, 3, 59, 0]), 'item': np.array([24, 1, 2])}
+    excl = {('user', 'buys', 'item'): np.array([0, 5, 9, 11]), ('item', 'bought-by', 'user'): np.array([0, 5, 9, 11])}
+    for key, ex in ((12345, None), (2 ** 62 + 17, excl)):
+        blocks = sampler.sample_blocks(g, seeds, key=key, exclude=ex)
+        assert_blocks_equal_oracle(blocks, oracle_blocks(g, sampler, seeds, key, ex), g)
+        for b in blocks:  # excluded edges never show up, fan-out bound holds
+            for c, r in b.rels.items():
+                if ex and c in ex:
+                    assert not set(r.eperm.tolist()) & set(ex[c].tolist())
+                if fanouts:
+                    assert int(np.diff(r.indptr.numpy()).max(initial=0)) <= max(fanouts)
+
+
+def test_fanout_sampling_is_uniform_without_replacement():
+    """Every in-edge of a row is kept with probability fanout / degree (over keys); never twice in one draw."""
+    src = np.arange(40) % 13
+    g = grb.HeteroGraph({('user', 'buys', 'item'): (src, np.zeros(40, np.int64))}, {'user': 13, 'item': 1})
+    sampler = grb.MultiLayerNeighborSampler([8])
+    hits = np.zeros(40)
+    n = 600
+    for key in range(n):
+        r = sampler.sample_blocks(g, {'item': np.array([0])}, key=key)[0].rels[('user', 'buys', 'item')]
+        e = r.eperm.numpy()
+        assert e.size == 8 and np.unique(e).size == 8 and np.all(np.diff(e) > 0)
+        hits[e] += 1
+    p = hits / n
+    assert abs(p.mean() - 0.2) < 1e-9 and np.all(np.abs(p - 0.2) < 5 * np.sqrt(0.2 * 0.8 / n))
+
+
+def test_negative_sampler_matches_oracle_and_is_uniform():
+    d, g = small_graph(6, 500)
+    c = ('user', 'clicks', 'item')
+    eids = np.array([3, 0, 17, 3])
+    got = grb.negative_sampler.Uniform(7)(g, {'clicks': eids}, 99)[c]
+    want = O.negative_uniform(g.edge_arrays(c)[0], eids, 7, g.num_nodes('item'), O.sample_key(99, 4096 + g.canonical_etypes.index(c)))
+    assert got[0].tolist() == want[0].tolist() and got[1].tolist() == want[1].tolist()
+    big = grb.negative_sampler.Uniform(2000)(g, {'clicks': np.arange(50)}, 5)[c][1]
+    counts = np.bincount(big, minlength=25)
+    assert counts.sum() == 100000 and np.all(np.abs(counts - 4000) < 5 * np.sqrt(4000))
+
+
+def test_device_block_builder_host_logic_with_oracle_kernels(monkeypatch):
+    """The Python orchestration of ``sampling_device.py`` (buffer offsets, remap splitting, block assembly) with the
+    four C-ABI calls it makes replaced by the ORACLE's restatements, on CPU tensors: must equal the host builder.
+    (The kernels themselves are checked against the same oracle functions on the GPU, tests/test_gpu_parity.py.)"""
+    import importlib
+    sd_mod = importlib.import_module('gnn_recsys_b200.sampling_device')
+    ops = grb.ops
+    cpu = torch.device('cpu')
+
+    def fake_count(indptr, eperm, seeds, fanout, excl=None):
+        ip, _, _ = O.sample_frontier(indptr.numpy(), np.zeros(int(indptr[-1]), np.int64),
+                                     None if eperm is None else eperm.numpy(), seeds.numpy(), fanout, 0,
+                                     () if excl is None else excl.numpy())
+        return torch.from_numpy(ip), torch.tensor([int(ip[-1])], dtype=torch.int32)
+
+    def fake_fill(indptr, indices, eperm, seeds, fanout, excl, key, out_indptr, out_src, out_eid):
+        ip, s, e = O.sample_frontier(indptr.numpy(), indices.numpy(), None if eperm is None else eperm.numpy(),
+                                     seeds.numpy(), fanout, key, () if excl is None else excl.numpy())
+        assert ip.tolist() == out_indptr.tolist()
+        out_src.copy_(torch.from_numpy(s))
+        out_eid.copy_(torch.from_numpy(e))
+
+    def fake_neg(edge_src, eids, k, n_dst_nodes, key):
+        s, d = O.negative_uniform(edge_src.numpy(), eids.numpy(), k, n_dst_nodes, key)
+        return torch.from_numpy(s), torch.from_numpy(d)
+
+    def fake_remap(raw):
+        ids, uniq = O.first_appearance_ids(raw.tolist())
+        return torch.from_numpy(ids.astype(np.int32)), torch.tensor(uniq, dtype=torch.int64)
+
+    def fake_full_block_on(self, device, edge_weight=None):
+        return self.full_block(edge_weight, with_features=False)
+
+    def fake_device_edges(self, etype, device):
+        s, d = self.edge_arrays(etype)
+        return torch.from_numpy(s.astype(np.int32)), torch.from_numpy(d.astype(np.int32))
+
+    monkeypatch.setattr(ops, 'sample_count', fake_count)
+    monkeypatch.setattr(ops, 'sample_fill', fake_fill)
+    monkeypatch.setattr(ops, 'negative_uniform', fake_neg)
+    monkeypatch.setattr(ops, 'remap_first_appearance', fake_remap)
+    monkeypatch.setattr(grb.HeteroGraph, 'full_block_on', fake_full_block_on)
+    monkeypatch.setattr(grb.HeteroGraph, 'device_edges', fake_device_edges)
+
+    d, g = small_graph(8, 1500)
+    rng = np.random.default_rng(0)
+    for fwd, bwd in (('buys', 'bought-by'), ('clicks', 'clicked-by')):
+        occ = torch.from_numpy(rng.integers(1, 5, g.num_edges(fwd)).astype(np.float32))
+        g.edges[fwd].data['occurrence'], g.edges[bwd].data['occurrence'] = occ, occ
+    rev = {'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by', 'clicked-by': 'clicks'}
+    eids = {'buys': np.arange(g.num_edges('buys')), 'clicks': np.arange(g.num_edges('clicks'))}
+    for sampler in (grb.MultiLayerNeighborSampler([4, 3]), grb.MultiLayerFullNeighborSampler(2)):
+        kw = dict(exclude='reverse_types', reverse_etypes=rev, negative_sampler=grb.negative_sampler.Uniform(6),
+                  batch_size=40, shuffle=True, seed=3)
+        host = grb.EdgeDataLoader(g, eids, sampler, **kw)
+        devl = grb.EdgeDataLoader(g, eids, sampler, **kw)
+        it_h = iter(host)
+        order = devl.rng.permutation(devl._flat_e.size)
+        for b in range(2):
+            in_h, pos_h, neg_h, blocks_h = next(it_h)
+            # drive the device builder directly (the loader's own dispatch insists on a CUDA device)
+            sel = order[b * 40:(b + 1) * 40]
+            items = {c: devl._flat_e[sel[devl._flat_t[sel] == i]] for i, c in enumerate(devl._types)}
+            items = {c: e for c, e in items.items() if e.size}
+            key = int(devl.rng.integers(0, 2 ** 63, dtype=np.int64))
+            in_d, pos_d, neg_d, blocks_d = sd_mod.edge_batch_device(devl, items, key, cpu)
+            for c in g.canonical_etypes:
+                for a, b in ((pos_h, pos_d), (neg_h, neg_d)):
+                    for x, y in zip(a.edge_arrays(c), b.edge_arrays(c)):
+                        assert x.tolist() == y.tolist()
+            for bh, bd in zip(blocks_h, blocks_d):
+                assert bh.num_src == bd.num_src and bh.num_dst == bd.num_dst
+                for c in g.canonical_etypes:
+                    rh, rd = bh.rels[c], bd.rels[c]
+                    assert rh.indptr.tolist() == rd.indptr.tolist() and rh.indices.tolist() == rd.indices.tolist()
+                    assert rh.eperm.tolist() == rd.eperm.tolist() and (rh.n_src, rh.n_dst) == (rd.n_src, rd.n_dst)
+                for t in g.ntypes:
+                    assert torch.equal(bh.srcnodes[t].data['features'], bd.srcnodes[t].data['features'])
+                    assert bh.srcnodes[t].data[grb.NID].tolist() == bd.srcnodes[t].data[grb.NID].tolist()
+                    assert bh.dstnodes[t].data[grb.NID].tolist() == bd.dstnodes[t].data[grb.NID].tolist()
+    # edge weights gathered by edge id (the *_edge aggregators): node-loader blocks, host vs device builder
+    seeds = {'user': np.array([5, 1, 40]), 'item': np.array([3, 2])}
+    s = grb.MultiLayerNeighborSampler([5, 5])
+    bh = s.sample_blocks(g, seeds, key=77, edge_weight='occurrence')
+    bd = sd_mod.sample_blocks_device(g, s, seeds, 77, cpu, None, 'occurrence')
+    for x, y in zip(bh, bd):
+        for c in g.canonical_etypes:
+            assert x.rels[c].indices.tolist() == y.rels[c].indices.tolist()
+            assert torch.equal(x.rels[c].weight, y.rels[c].weight)
