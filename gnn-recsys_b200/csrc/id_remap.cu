@@ -73,7 +73,7 @@ __global__ void assign_kernel(const long long* __restrict__ raw, long long n, co
   }
 }
 
-struct Layout { size_t keys, vals, first, rank, total; long long cap; };
+struct Layout { size_t keys, vals, first, rank, tiles, total; long long cap; };
 Layout layout(int64_t n) {
   Layout l;
   long long cap = 1024;
@@ -85,6 +85,7 @@ Layout layout(int64_t n) {
   l.vals = take(4 * (size_t)cap);
   l.first = take(4 * (size_t)std::max<int64_t>(n, 1));
   l.rank = take(4 * (size_t)std::max<int64_t>(n, 1));
+  l.tiles = take(gr::scan_workspace_bytes(std::max<int64_t>(n, 1)));
   l.total = off;
   return l;
 }
@@ -120,8 +121,7 @@ extern "C" int gr_remap_first_appearance_i64(const int64_t* raw, int64_t n, int3
   GR_LAUNCH_CHECK();
   flag_first_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, keys, vals, mask, first, rank);
   GR_LAUNCH_CHECK();
-  gr::scan1_kernel<<<1, 1024, 0, st>>>(rank, n, n_unique);
-  GR_LAUNCH_CHECK();
+  GR_CUDA(gr::scan_exclusive_i32(rank, n, n_unique, reinterpret_cast<int*>(base + l.tiles), st));
   assign_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, first, rank, new_ids,
                                       reinterpret_cast<long long*>(uniq_raw_or_null));
   GR_LAUNCH_CHECK();

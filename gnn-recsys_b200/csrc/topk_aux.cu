@@ -47,13 +47,32 @@ __global__ void __launch_bounds__(256) colmean_partial_kernel(const float* __res
   }
 }
 
-__global__ void colmean_final_kernel(const float* __restrict__ partials, long long n_partials, long long n, int d,
-                                     float* __restrict__ center) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  float a = 0.f;
-  for (long long p = 0; p < n_partials; ++p) a += partials[p * d + c];
-  center[c] = n > 0 ? a / (float)n : 0.f;
+// one block = 32 columns x 32 warps: warp w sums partial rows w, w + 32, ... (coalesced 128-byte reads, 4 independent
+// loads in flight), then the 32 per-warp sums are added in warp order -- a fixed order, so the centre is deterministic
+__global__ void __launch_bounds__(1024) colmean_final_kernel(const float* __restrict__ partials, long long n_partials,
+                                                             long long n, int d, float* __restrict__ center) {
+  __shared__ float s_part[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < d) {
+    long long p = w;
+    for (; p + 96 < n_partials; p += 128) {
+      a0 += partials[p * d + c];
+      a1 += partials[(p + 32) * d + c];
+      a2 += partials[(p + 64) * d + c];
+      a3 += partials[(p + 96) * d + c];
+    }
+    for (; p < n_partials; p += 32) a0 += partials[p * d + c];
+  }
+  s_part[w][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && c < d) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a += s_part[i][lane];
+    center[c] = n > 0 ? a / (float)n : 0.f;
+  }
 }
 
 int colmean_grid() { return gr::sm_count() * 4; }
@@ -483,7 +502,7 @@ extern "C" int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, f
   float* partials = static_cast<float*>(ws);
   colmean_partial_kernel<<<grid, 256, 0, st>>>(x, n, d, partials);
   GR_LAUNCH_CHECK();
-  colmean_final_kernel<<<(d + 127) / 128, 128, 0, st>>>(partials, (long long)grid * 8, n, d, center);
+  colmean_final_kernel<<<(d + 31) / 32, 1024, 0, st>>>(partials, (long long)grid * 8, n, d, center);
   GR_LAUNCH_CHECK();
   return GR_OK;
 }

@@ -194,9 +194,10 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_dst: int):
     return indptr, indices, eperm
 
 
-def remap_first_appearance(raw: torch.Tensor):
+def remap_first_appearance(raw: torch.Tensor, defer: bool = False):
     """Raw int64 ids -> ``(new_ids int32 [n], uniq_raw int64 [n_unique])``: contiguous ids in order of first
-    appearance (``create_ids``, reference ``src/builder.py:182-227``)."""
+    appearance (``create_ids``, reference ``src/builder.py:182-227``). ``defer=True`` skips the host read of the count
+    and returns ``(new_ids, uniq_raw buffer [n], n_unique device int32 [1])``."""
     assert raw.dtype == torch.int64
     n = int(raw.shape[0])
     dev = raw.device
@@ -207,7 +208,18 @@ def remap_first_appearance(raw: torch.Tensor):
     ws = N.workspace(lib.gr_remap_workspace_bytes(n), dev)
     N.call('gr_remap_first_appearance_i64', N.ptr(raw), n, N.ptr(new_ids), N.ptr(uniq), N.ptr(n_unique), N.ptr(ws),
            ws.numel(), N.stream())
+    if defer:
+        return new_ids, uniq, n_unique
     return new_ids, uniq[:int(n_unique.item())]
+
+
+def remap_many(raws):
+    """``remap_first_appearance`` of several id arrays with ONE host read of their unique counts."""
+    outs = [remap_first_appearance(r, defer=True) for r in raws]
+    if not outs:
+        return []
+    counts = torch.cat([o[2] for o in outs]).tolist()
+    return [(o[0], o[1][:c]) for o, c in zip(outs, counts)]
 
 
 def sample_count(indptr: torch.Tensor, eperm: Optional[torch.Tensor], seeds: torch.Tensor, fanout: int,

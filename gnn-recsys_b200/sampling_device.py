@@ -64,7 +64,7 @@ def sample_blocks_device(g: HeteroGraph, sampler, seed_nodes, key: int, device: 
         totals = torch.cat([v[2] for v in counted.values()]).tolist() if counted else []  # the layer's one host read
         totals = dict(zip(counted.keys(), totals))
         rels, src_ids, num_src = {}, {}, {}
-        local_of = {}
+        local_of, bufs = {}, []
         for t in g.ntypes:
             mine = [c for c in cets if c[0] == t and c in counted]
             n_seed = int(seeds[t].numel()) if t in seeds else 0
@@ -85,9 +85,12 @@ def sample_blocks_device(g: HeteroGraph, sampler, seed_nodes, key: int, device: 
                                     sample_key(key, layer * 64 + ci), out_indptr, buf[off:off + n], eid)
                 local_of[c] = (off, n, eid)
                 off += n
-            new_ids, uniq = ops.remap_first_appearance(buf)
+            bufs.append(buf)
+        for t, (new_ids, uniq) in zip(g.ntypes, ops.remap_many(bufs)):  # to_block; one host read for all node types
             src_ids[t], num_src[t] = uniq, int(uniq.numel())
-            for c in mine:
+            for c in cets:
+                if c[0] != t or c not in counted:
+                    continue
                 off, n, eid = local_of[c]
                 w = None
                 if full.rels[c].weight is not None:
@@ -137,18 +140,21 @@ def edge_batch_device(loader, items: Dict, key: int, device: torch.device):
             neg[c] = ops.negative_uniform(u_all, e, loader.neg.k, g.num_nodes(c[2]),
                                           sample_key(key, NEGATIVE_STREAM + cets.index(c)))
     # batch node space per type: first appearance over [pos, neg] x etypes x (src, dst)
-    space, local = {}, {}
+    space, local, cats, layout = {}, {}, [], []
     for t in g.ntypes:
         parts, slots = [], []
         for name, edges in (('pos', pos), ('neg', neg)):
             for c in cets:
                 if c in edges:
                     if c[0] == t:
-                        parts.append(edges[c][0]); slots.append((name, c, 0))
+                        parts.append(edges[c][0])
+                        slots.append((name, c, 0))
                     if c[2] == t:
-                        parts.append(edges[c][1]); slots.append((name, c, 1))
-        cat = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=device)
-        new_ids, uniq = ops.remap_first_appearance(cat)
+                        parts.append(edges[c][1])
+                        slots.append((name, c, 1))
+        cats.append(torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=device))
+        layout.append((parts, slots))
+    for t, (parts, slots), (new_ids, uniq) in zip(g.ntypes, layout, ops.remap_many(cats)):
         space[t] = uniq
         off = 0
         for part, slot in zip(parts, slots):

@@ -107,3 +107,73 @@ def test_topk_of_sampled_users_matches_the_brute_force_kernel(world):
     for r in sample[:300].tolist():                             # nothing already bought
         assert not set(ids[r].tolist()) & set(bought[r])
     assert int(n_over) < U // 100
+
+
+def test_device_frontier_properties_at_full_size(world):
+    """Fan-out frontier of 200k seed rows of the c2 graph (hub items with > 1M in-edges included), checked through
+    properties: per-seed count = min(fanout, degree); every kept (source, edge id) pair IS an in-edge of its seed;
+    edge ids strictly ascend within a row (no duplicates, CSR order); excluded edge ids never appear; same key ->
+    same frontier, other key -> another one; the hub row keeps exactly `fanout` edges."""
+    grb, dev, g, blk = world['grb'], world['dev'], world['g'], world['blk']
+    c = ('user', 'clicks', 'item')
+    rel = blk.rels[c]
+    s, d = g.edge_arrays(c)
+    src_all = torch.from_numpy(s.astype(np.int64)).to(dev)
+    dst_all = torch.from_numpy(d.astype(np.int64)).to(dev)
+    deg = (rel.indptr[1:] - rel.indptr[:-1]).long()
+    gen = torch.Generator(device=dev).manual_seed(0)
+    seeds = torch.randperm(I, device=dev, generator=gen)[:I]
+    hub = int(torch.argmax(deg))
+    assert int(deg[hub]) > 100_000
+    excl = torch.unique(torch.randint(0, rel.nnz, (4000,), device=dev, generator=gen)).to(torch.int32)
+    fan = 10
+    out = {}
+    for name, key, ex in (('a', grb.sample_key(5, 1), None), ('a2', grb.sample_key(5, 1), None),
+                          ('b', grb.sample_key(6, 1), None), ('x', grb.sample_key(5, 1), excl)):
+        out_indptr, total = grb.ops.sample_count(rel.indptr, rel.eperm, seeds, fan, ex)
+        n = int(total.item())
+        o_src = torch.empty(n, dtype=torch.int64, device=dev)
+        o_eid = torch.empty(n, dtype=torch.int32, device=dev)
+        grb.ops.sample_fill(rel.indptr, rel.indices, rel.eperm, seeds, fan, ex, key, out_indptr, o_src, o_eid)
+        out[name] = (out_indptr, o_src, o_eid)
+        cnt = (out_indptr[1:] - out_indptr[:-1]).long()
+        e = o_eid.long()
+        row_of = torch.repeat_interleave(seeds, cnt)
+        assert torch.equal(dst_all[e], row_of) and torch.equal(src_all[e], o_src)       # real in-edges of their seeds
+        inner = torch.ones(n, dtype=torch.bool, device=dev)
+        inner[out_indptr[:-1].long()[cnt > 0]] = False
+        assert bool((e[1:] > e[:-1])[inner[1:]].all())                                    # ascending, duplicate-free
+        if ex is None:
+            assert torch.equal(cnt, torch.clamp(deg[seeds], max=fan))
+        else:
+            assert not bool(torch.isin(e, ex.long()).any())
+            assert bool((cnt <= torch.clamp(deg[seeds], max=fan)).all())
+        assert int(cnt[seeds == hub]) == fan
+    assert all(torch.equal(x, y) for x, y in zip(out['a'], out['a2']))
+    assert not torch.equal(out['a'][2], out['b'][2])
+    # full neighbourhood of a few seeds (fanout 0) == the CSR slices
+    few = torch.tensor([hub, int(seeds[0]), int(torch.nonzero(deg == 0).flatten()[0])], device=dev)
+    out_indptr, total = grb.ops.sample_count(rel.indptr, rel.eperm, few, 0)
+    n = int(total.item())
+    o_src = torch.empty(n, dtype=torch.int64, device=dev)
+    o_eid = torch.empty(n, dtype=torch.int32, device=dev)
+    grb.ops.sample_fill(rel.indptr, rel.indices, rel.eperm, few, 0, None, 0, out_indptr, o_src, o_eid)
+    want = torch.cat([rel.eperm[int(rel.indptr[r]):int(rel.indptr[r + 1])] for r in few.tolist()])
+    assert torch.equal(o_eid, want) and n == int(deg[few].sum())
+
+
+def test_negative_sampler_uniform_at_full_size(world):
+    """2.56M negatives (1024 positives x 2500, the reference default): sources repeat the positive's source k times,
+    destinations cover the item range uniformly (chi-square within 6 sigma)."""
+    grb, dev, g = world['grb'], world['dev'], world['g']
+    c = ('user', 'buys', 'item')
+    u_all, _ = g.device_edges(c, dev)
+    eids = torch.arange(0, 1024 * 977, 977, device=dev, dtype=torch.int64)
+    k = 2500
+    s, d = grb.ops.negative_uniform(u_all, eids, k, I, grb.sample_key(9, 4096))
+    assert torch.equal(s.view(1024, k), u_all[eids].long().unsqueeze(1).expand(1024, k))
+    assert int(d.min()) >= 0 and int(d.max()) < I
+    counts = torch.bincount(d, minlength=I).double()
+    expect = 1024 * k / I
+    chi2 = float(((counts - expect) ** 2 / expect).sum())
+    assert abs(chi2 - (I - 1)) < 6 * (2 * (I - 1)) ** 0.5

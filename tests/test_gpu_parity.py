@@ -660,3 +660,19 @@ def test_device_node_loader_minibatches_and_edge_weights(grb):
         got = grb.get_embeddings(g, 8, model, mini, len(mini), False, dev, True)
         for t in g.ntypes:
             np.testing.assert_allclose(got[t].numpy(), want[t].numpy(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize('shape', [(1, 128), (5000, 128), (20011, 64), (300, 256), (777, 100)])
+def test_colmean_normalized_vs_torch(grb, shape):
+    """The item 'centre' of the scoring stage: mean of the L2-normalised rows (zero rows stay zero), deterministic."""
+    n, d = shape
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, d, generator=g) * torch.rand(n, 1, generator=g) * 10
+    if n > 3:
+        x[3] = 0
+    xd = x.cuda()
+    c1 = grb.ops.colmean_normalized(xd)
+    c2 = grb.ops.colmean_normalized(xd)
+    assert torch.equal(c1, c2)
+    want = torch.nn.functional.normalize(x.double(), dim=1, eps=1e-12).mean(0)
+    np.testing.assert_allclose(c1.cpu().numpy(), want.numpy(), rtol=1e-4, atol=2e-7)

@@ -263,6 +263,7 @@ def test_device_block_builder_host_logic_with_oracle_kernels(monkeypatch):
     monkeypatch.setattr(ops, 'sample_fill', fake_fill)
     monkeypatch.setattr(ops, 'negative_uniform', fake_neg)
     monkeypatch.setattr(ops, 'remap_first_appearance', fake_remap)
+    monkeypatch.setattr(ops, 'remap_many', lambda raws: [fake_remap(r) for r in raws])
     monkeypatch.setattr(grb.HeteroGraph, 'full_block_on', fake_full_block_on)
     monkeypatch.setattr(grb.HeteroGraph, 'device_edges', fake_device_edges)
 
