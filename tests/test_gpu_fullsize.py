@@ -152,7 +152,7 @@ def test_device_frontier_properties_at_full_size(world):
     assert all(torch.equal(x, y) for x, y in zip(out['a'], out['a2']))
     assert not torch.equal(out['a'][2], out['b'][2])
     # full neighbourhood of a few seeds (fanout 0) == the CSR slices
-    few = torch.tensor([hub, int(seeds[0]), int(torch.nonzero(deg == 0).flatten()[0])], device=dev)
+    few = torch.tensor([hub, int(seeds[0]), int(torch.argmin(deg))], device=dev)
     out_indptr, total = grb.ops.sample_count(rel.indptr, rel.eperm, few, 0)
     n = int(total.item())
     o_src = torch.empty(n, dtype=torch.int64, device=dev)
