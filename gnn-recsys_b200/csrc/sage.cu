@@ -83,54 +83,84 @@ __device__ __forceinline__ void combine(float4& a, const float4& v) {
 }
 
 // Warp-cooperative reduce of neighbour rows for CSR slots [e0, e1) into acc (pre-initialised by the caller).
-// Lane l owns columns 4*(l + 32q) .. +3 for q < VN.
+// Lane l owns columns 4*(l + 32q) .. +3 for q < VN; lanes whose columns lie beyond d read column block 0 instead (no
+// predicate in the loop) and their accumulators are meaningless -- callers clear them (clear_tail_lanes).
+// Neighbours are consumed in groups of exactly N in {8, 4, 2, 1} (warp-uniform branches, N independent 128-bit loads in
+// flight, no padded slots), in CSR order: the sum order is the sequential order of the oracle.
+template <int N, int VN, bool MAXR>
+__device__ __forceinline__ void gather_group(const float* __restrict__ h, int d, int my, float myw, bool weighted,
+                                             int j, const int (&coff)[VN], float4 (&acc)[VN]) {
+  float4 v[N][VN];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const int s = __shfl_sync(FULL, my, j + u);
+    const float* row = h + (size_t)s * d;
+#pragma unroll
+    for (int q = 0; q < VN; ++q) v[u][q] = gr::ldg_f4(row + coff[q]);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    if (weighted) {
+      const float w = __shfl_sync(FULL, myw, j + u);
+#pragma unroll
+      for (int q = 0; q < VN; ++q) {
+        v[u][q].x = __fmul_rn(v[u][q].x, w); v[u][q].y = __fmul_rn(v[u][q].y, w);
+        v[u][q].z = __fmul_rn(v[u][q].z, w); v[u][q].w = __fmul_rn(v[u][q].w, w);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < VN; ++q) combine<MAXR>(acc[q], v[u][q]);
+  }
+}
+
 template <int VN, bool MAXR>
 __device__ __forceinline__ void gather_range(const int* __restrict__ indices, const float* __restrict__ ew,
                                              const float* __restrict__ h, int d, int e0, int e1, int lane,
                                              float4 (&acc)[VN]) {
   constexpr int UNROLL = (VN == 1) ? 8 : 4;
+  int coff[VN];
+#pragma unroll
+  for (int q = 0; q < VN; ++q) {
+    const int c = (lane + 32 * q) * 4;
+    coff[q] = c < d ? c : 0;
+  }
+  const bool weighted = ew != nullptr;
   for (int e = e0; e < e1; e += 32) {
     const int cnt = min(32, e1 - e);
     const int my = lane < cnt ? gr::ldg_stream_i32(indices + e + lane) : 0;
     float myw = 1.f;
-    if (ew != nullptr) myw = lane < cnt ? gr::ldg_stream_f32(ew + e + lane) : 0.f;
-    for (int j = 0; j < cnt; j += UNROLL) {
-      float4 v[UNROLL][VN];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int s = __shfl_sync(FULL, my, (j + u) & 31);
-        const float* row = h + (size_t)s * d;
-#pragma unroll
-        for (int q = 0; q < VN; ++q) {
-          const int c = (lane + 32 * q) * 4;
-          v[u][q] = (j + u < cnt && c < d) ? gr::ldg_f4(row + c) : ident4<MAXR>();
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        if (ew != nullptr) {
-          const float w = __shfl_sync(FULL, myw, (j + u) & 31);
-          if (j + u < cnt) {
-#pragma unroll
-            for (int q = 0; q < VN; ++q) {
-              v[u][q].x = __fmul_rn(v[u][q].x, w); v[u][q].y = __fmul_rn(v[u][q].y, w);
-              v[u][q].z = __fmul_rn(v[u][q].z, w); v[u][q].w = __fmul_rn(v[u][q].w, w);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < VN; ++q) combine<MAXR>(acc[q], v[u][q]);
-      }
-    }
+    if (weighted) myw = lane < cnt ? gr::ldg_stream_f32(ew + e + lane) : 0.f;
+    int j = 0;
+    for (; j + UNROLL <= cnt; j += UNROLL) gather_group<UNROLL, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc);
+    const int rem = cnt - j;
+    if (UNROLL == 8 && (rem & 4)) { gather_group<4, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc); j += 4; }
+    if (rem & 2) { gather_group<2, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc); j += 2; }
+    if (rem & 1) gather_group<1, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc);
   }
 }
 
-template <bool MAXR>
+// accumulators of lanes whose columns lie beyond d (see gather_range) -> 0
+template <int VN>
+__device__ __forceinline__ void clear_tail_lanes(float4 (&acc)[VN], int d, int lane) {
+#pragma unroll
+  for (int q = 0; q < VN; ++q)
+    if ((lane + 32 * q) * 4 >= d) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// EXACT: IEEE division by the degree (bit-identical to `sum / clamp(deg, 1)`, used by the stand-alone gather);
+// otherwise one correctly rounded reciprocal per row and four multiplies (<= 1 ulp apart; the fused kernel's split-MMA
+// projection that follows is itself only fp32-accurate, far inside rtol 1e-4).
+template <bool MAXR, bool EXACT = true>
 __device__ __forceinline__ float4 finalize4(float4 a, int deg) {
   if (deg == 0) return make_float4(0.f, 0.f, 0.f, 0.f);
   if (!MAXR) {
     const float f = (float)deg;
-    a.x = a.x / f; a.y = a.y / f; a.z = a.z / f; a.w = a.w / f;
+    if (EXACT) {
+      a.x = a.x / f; a.y = a.y / f; a.z = a.z / f; a.w = a.w / f;
+    } else {
+      const float r = __frcp_rn(f);
+      a.x *= r; a.y *= r; a.z *= r; a.w *= r;
+    }
   }
   return a;
 }
@@ -164,7 +194,8 @@ __device__ __forceinline__ void reduce_row_regs(const int* __restrict__ indptr, 
     for (int q = 0; q < VN; ++q) acc[q] = ident4<MAXR>();
     gather_range<VN, MAXR>(indices, ew, h, d, beg, end, lane, acc);
 #pragma unroll
-    for (int q = 0; q < VN; ++q) acc[q] = finalize4<MAXR>(acc[q], deg);
+    for (int q = 0; q < VN; ++q) acc[q] = finalize4<MAXR, false>(acc[q], deg);
+    clear_tail_lanes<VN>(acc, d, lane);
   }
 }
 __device__ __forceinline__ float absmax4(const float4& v) {
@@ -498,19 +529,17 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
       for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
   const float4* wp = p.packed + (size_t)(cg * NT) * 32 + lane;
   float4 bq[NT];
-#pragma unroll
-  for (int n = 0; n < NT; ++n) bq[n] = __ldg(wp + (size_t)n * 32);
   if (F16) {
     const int ks16_self = p.ds / 16, ks16_all = (p.ds + p.dn) / 16;
-    for (int ks = 0; ks < ks16_all; ++ks) {
-      float4 bcur[NT];
+    // B fragments double-buffered in two register sets (no copies): while k-step ks runs on one set the loads of
+    // k-step ks + 1 (L1 / L2 resident) fill the other
+    float4 bq2[NT];
+    auto load_b = [&](float4 (&b)[NT], int ks) {
+      const float4* src = wp + (size_t)ks * n_tiles * 32;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) bcur[n] = bq[n];
-      if (ks + 1 < ks16_all) {
-        const float4* nx = wp + (size_t)(ks + 1) * n_tiles * 32;
-#pragma unroll
-        for (int n = 0; n < NT; ++n) bq[n] = __ldg(nx + (size_t)n * 32);
-      }
+      for (int n = 0; n < NT; ++n) b[n] = __ldg(src + (size_t)n * 32);
+    };
+    auto kstep = [&](int ks, const float4 (&b)[NT]) {
       const float* tile = ks < ks16_self ? sS : sN;
       const int pitch = ks < ks16_self ? ps : pn;
       const int kc = (ks < ks16_self ? ks : ks - ks16_self) * 16 + 2 * tig;
@@ -526,15 +555,26 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
         split_f16x2(x3.x, x3.y, ah[3], al[3]);
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-          const uint32_t bh0 = __float_as_uint(bcur[n].x), bh1 = __float_as_uint(bcur[n].y);
-          const uint32_t bl0 = __float_as_uint(bcur[n].z), bl1 = __float_as_uint(bcur[n].w);
+          const uint32_t bh0 = __float_as_uint(b[n].x), bh1 = __float_as_uint(b[n].y);
+          const uint32_t bl0 = __float_as_uint(b[n].z), bl1 = __float_as_uint(b[n].w);
           mma_f16(acc[m][n], al, bh0, bh1);
           mma_f16(acc[m][n], ah, bl0, bl1);
           mma_f16(acc[m][n], ah, bh0, bh1);
         }
       }
+    };
+    load_b(bq, 0);
+    for (int ks = 0; ks < ks16_all; ks += 2) {
+      if (ks + 1 < ks16_all) load_b(bq2, ks + 1);
+      kstep(ks, bq);
+      if (ks + 1 < ks16_all) {
+        if (ks + 2 < ks16_all) load_b(bq, ks + 2);
+        kstep(ks + 1, bq2);
+      }
     }
-  } else
+  } else {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) bq[n] = __ldg(wp + (size_t)n * 32);
   for (int ks = 0; ks < ks_all; ++ks) {
     float4 bcur[NT];
 #pragma unroll
@@ -564,6 +604,7 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
         mma_tf32(acc[m][n], ah, bh0, bh1);
       }
     }
+  }
   }
 
   // relu + row sum of squares: a row's columns live in 4 lanes (tig) x 4 warps (cg)
@@ -598,10 +639,10 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
     for (int h = 0; h < 2; ++h) {
       const int r = m * 16 + h * 8 + g;
       const int64_t row = row0 + r;
-      float nrm = 1.f;
+      float inv_nrm = 1.f;  // z / (|z| or 1 if 0) as z * rcp(|z|): one correctly rounded reciprocal per row
       if (p.l2norm) {
-        nrm = sqrtf((s_part[0][r] + s_part[1][r]) + (s_part[2][r] + s_part[3][r]));
-        if (nrm == 0.f) nrm = 1.f;
+        const float nrm = sqrtf((s_part[0][r] + s_part[1][r]) + (s_part[2][r] + s_part[3][r]));
+        inv_nrm = nrm == 0.f ? 1.f : __frcp_rn(nrm);
       }
       float unscale = 1.f;
       if (F16 && !p.l2norm) unscale = s_inv[r] * __ldg(p.wscale + 1);  // exact powers of two
@@ -610,7 +651,7 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
         for (int n = 0; n < NT; ++n) {
           float* o = p.out + (size_t)row * p.dout + cg * (NT * 8) + n * 8 + 2 * tig;
           float z0 = acc[m][n][2 * h], z1 = acc[m][n][2 * h + 1];
-          if (p.l2norm) { z0 = z0 / nrm; z1 = z1 / nrm; }
+          if (p.l2norm) { z0 *= inv_nrm; z1 *= inv_nrm; }
           else if (F16) { z0 *= unscale; z1 *= unscale; }
           if (p.accumulate == GR_ACC_ADD) {
             const float2 prev = *reinterpret_cast<const float2*>(o);
