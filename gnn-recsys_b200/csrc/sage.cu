@@ -73,12 +73,32 @@ __device__ __forceinline__ float4 ident4() {
   return make_float4(v, v, v, v);
 }
 
+// sm_100 packed fp32 pairs (add.rn.f32x2 / mul.rn.f32x2): two IEEE round-to-nearest results per instruction --
+// bit-identical to the scalar forms, half the issue slots of the gather loop.
+__device__ __forceinline__ void add2_rn(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rb, {%2, %3};\n\t"
+      "add.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2_rn(float& a0, float& a1, float w) {
+  asm("{\n\t.reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rb, {%2, %2};\n\t"
+      "mul.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(w));
+}
+
 template <bool MAXR>
 __device__ __forceinline__ void combine(float4& a, const float4& v) {
   if (MAXR) {
     a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
   } else {
-    a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
+    add2_rn(a.x, a.y, v.x, v.y);
+    add2_rn(a.z, a.w, v.z, v.w);
   }
 }
 
@@ -87,16 +107,17 @@ __device__ __forceinline__ void combine(float4& a, const float4& v) {
 // predicate in the loop) and their accumulators are meaningless -- callers clear them (clear_tail_lanes).
 // Neighbours are consumed in groups of exactly N in {8, 4, 2, 1} (warp-uniform branches, N independent 128-bit loads in
 // flight, no padded slots), in CSR order: the sum order is the sequential order of the oracle.
+// `hb[q]` = byte address of this lane's column block q in row 0; a neighbour row adds id * row_bytes (one IMAD.WIDE.U32).
 template <int N, int VN, bool MAXR>
-__device__ __forceinline__ void gather_group(const float* __restrict__ h, int d, int my, float myw, bool weighted,
-                                             int j, const int (&coff)[VN], float4 (&acc)[VN]) {
+__device__ __forceinline__ void gather_group(const char* const (&hb)[VN], unsigned row_bytes, int my, float myw,
+                                             bool weighted, int j, float4 (&acc)[VN]) {
   float4 v[N][VN];
 #pragma unroll
   for (int u = 0; u < N; ++u) {
-    const int s = __shfl_sync(FULL, my, j + u);
-    const float* row = h + (size_t)s * d;
+    const unsigned s = (unsigned)__shfl_sync(FULL, my, j + u);
+    const size_t off = (size_t)s * row_bytes;
 #pragma unroll
-    for (int q = 0; q < VN; ++q) v[u][q] = gr::ldg_f4(row + coff[q]);
+    for (int q = 0; q < VN; ++q) v[u][q] = __ldg(reinterpret_cast<const float4*>(hb[q] + off));
   }
 #pragma unroll
   for (int u = 0; u < N; ++u) {
@@ -104,8 +125,8 @@ __device__ __forceinline__ void gather_group(const float* __restrict__ h, int d,
       const float w = __shfl_sync(FULL, myw, j + u);
 #pragma unroll
       for (int q = 0; q < VN; ++q) {
-        v[u][q].x = __fmul_rn(v[u][q].x, w); v[u][q].y = __fmul_rn(v[u][q].y, w);
-        v[u][q].z = __fmul_rn(v[u][q].z, w); v[u][q].w = __fmul_rn(v[u][q].w, w);
+        mul2_rn(v[u][q].x, v[u][q].y, w);
+        mul2_rn(v[u][q].z, v[u][q].w, w);
       }
     }
 #pragma unroll
@@ -118,12 +139,13 @@ __device__ __forceinline__ void gather_range(const int* __restrict__ indices, co
                                              const float* __restrict__ h, int d, int e0, int e1, int lane,
                                              float4 (&acc)[VN]) {
   constexpr int UNROLL = (VN == 1) ? 8 : 4;
-  int coff[VN];
+  const char* hb[VN];
 #pragma unroll
   for (int q = 0; q < VN; ++q) {
     const int c = (lane + 32 * q) * 4;
-    coff[q] = c < d ? c : 0;
+    hb[q] = reinterpret_cast<const char*>(h + (c < d ? c : 0));
   }
+  const unsigned row_bytes = (unsigned)d * 4u;
   const bool weighted = ew != nullptr;
   for (int e = e0; e < e1; e += 32) {
     const int cnt = min(32, e1 - e);
@@ -131,11 +153,11 @@ __device__ __forceinline__ void gather_range(const int* __restrict__ indices, co
     float myw = 1.f;
     if (weighted) myw = lane < cnt ? gr::ldg_stream_f32(ew + e + lane) : 0.f;
     int j = 0;
-    for (; j + UNROLL <= cnt; j += UNROLL) gather_group<UNROLL, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc);
+    for (; j + UNROLL <= cnt; j += UNROLL) gather_group<UNROLL, VN, MAXR>(hb, row_bytes, my, myw, weighted, j, acc);
     const int rem = cnt - j;
-    if (UNROLL == 8 && (rem & 4)) { gather_group<4, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc); j += 4; }
-    if (rem & 2) { gather_group<2, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc); j += 2; }
-    if (rem & 1) gather_group<1, VN, MAXR>(h, d, my, myw, weighted, j, coff, acc);
+    if (UNROLL == 8 && (rem & 4)) { gather_group<4, VN, MAXR>(hb, row_bytes, my, myw, weighted, j, acc); j += 4; }
+    if (rem & 2) { gather_group<2, VN, MAXR>(hb, row_bytes, my, myw, weighted, j, acc); j += 2; }
+    if (rem & 1) gather_group<1, VN, MAXR>(hb, row_bytes, my, myw, weighted, j, acc);
   }
 }
 
@@ -209,6 +231,8 @@ __device__ __forceinline__ float pow2_scale(float m) {
   e = max(min(254 - e, 200), 54);
   return __int_as_float(e << 23);
 }
+// 1 / s for s = pow2_scale(.) (a normal power of two with exponent field in [54, 200]): exact, no division
+__device__ __forceinline__ float pow2_inverse(float s) { return __int_as_float((254 - (__float_as_int(s) >> 23)) << 23); }
 
 // Reduced neighbour row of `row` -> dst (shared or global, 16-byte aligned rows of d floats).
 template <int VN, bool MAXR>
@@ -373,6 +397,16 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+__device__ __forceinline__ void split_f16x4(const float4& v, uint2& hi, uint2& lo) {
+  split_f16x2(v.x, v.y, hi.x, lo.x);
+  split_f16x2(v.z, v.w, hi.y, lo.y);
+}
+// four 8x8 b16 matrices -> the A fragment of mma.m16n8k16 (lane l supplies the address of row l % 16, k-half l / 16)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -452,8 +486,16 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
   const int pn = p.dn + PAD, ps = p.ds + PAD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp >> 2;                     // group of 4 warps
-  float* sN = smem + grp * R * (pn + ps);        // [R][dn + PAD]
-  float* sS = sN + R * pn;                       // [R][ds + PAD]
+  float* sN = smem + grp * R * (pn + ps);        // tf32 variant: [R][dn + PAD] fp32
+  float* sS = sN + R * pn;                       //               [R][ds + PAD] fp32
+  // fp16 variant: the same bytes hold FOUR half planes, split once by the gathering warp (the four warps of phase 2
+  // would otherwise each redo the split): neighbour hi / lo [R][dn + 8], self hi / lo [R][ds + 8] -- a 16-byte row pad
+  // makes both the 8-byte stores of phase 1 and the ldmatrix reads of phase 2 conflict-free
+  const int pnh = p.dn + 8, psh = p.ds + 8;
+  __half* sNh = reinterpret_cast<__half*>(sN);
+  __half* sNl = sNh + R * pnh;
+  __half* sSh = sNl + R * pnh;
+  __half* sSl = sSh + R * psh;
   __shared__ int s_next_[2], s_tile_[2];
   __shared__ float s_part_[2][4][R];
   __shared__ float s_inv_[2][R];                 // F16: 1 / row scale
@@ -481,12 +523,12 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
     const int64_t row = row0 + r;
     if (row < p.row_end) {
       float4 an[VN], as[VS];
-      reduce_row_regs<VN, MAXR>(p.indptr, p.indices, p.ew, p.h_src, p.dn, (int)row, lane, lw, an);
 #pragma unroll
-      for (int q = 0; q < VS; ++q) {
+      for (int q = 0; q < VS; ++q) {  // in flight while the neighbours are gathered
         const int c = (lane + 32 * q) * 4;
         as[q] = c < p.ds ? gr::ldg_f4(p.h_dst + (size_t)row * p.ds + c) : make_float4(0, 0, 0, 0);
       }
+      reduce_row_regs<VN, MAXR>(p.indptr, p.indices, p.ew, p.h_src, p.dn, (int)row, lane, lw, an);
       float sc = 1.f;
       if (F16) {  // one exact power-of-two scale per row, shared by its self and neighbour part
         float m = 0.f;
@@ -495,20 +537,47 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
 #pragma unroll
         for (int q = 0; q < VS; ++q) m = fmaxf(m, absmax4(as[q]));
         sc = pow2_scale(gr::warp_max(m));
-        if (lane == 0) s_inv[r] = 1.f / sc;
+        if (lane == 0) s_inv[r] = pow2_inverse(sc);
       }
 #pragma unroll
       for (int q = 0; q < VN; ++q) {
         const int c = (lane + 32 * q) * 4;
-        if (c < p.dn) *reinterpret_cast<float4*>(sN + r * pn + c) = F16 ? scale4(an[q], sc) : an[q];
+        if (c < p.dn) {
+          if (F16) {
+            uint2 hi, lo;
+            split_f16x4(scale4(an[q], sc), hi, lo);
+            *reinterpret_cast<uint2*>(sNh + r * pnh + c) = hi;
+            *reinterpret_cast<uint2*>(sNl + r * pnh + c) = lo;
+          } else {
+            *reinterpret_cast<float4*>(sN + r * pn + c) = an[q];
+          }
+        }
       }
 #pragma unroll
       for (int q = 0; q < VS; ++q) {
         const int c = (lane + 32 * q) * 4;
-        if (c < p.ds) *reinterpret_cast<float4*>(sS + r * ps + c) = F16 ? scale4(as[q], sc) : as[q];
+        if (c < p.ds) {
+          if (F16) {
+            uint2 hi, lo;
+            split_f16x4(scale4(as[q], sc), hi, lo);
+            *reinterpret_cast<uint2*>(sSh + r * psh + c) = hi;
+            *reinterpret_cast<uint2*>(sSl + r * psh + c) = lo;
+          } else {
+            *reinterpret_cast<float4*>(sS + r * ps + c) = as[q];
+          }
+        }
+      }
+    } else if (F16) {  // rows past the end of the shard: zero rows in all four half planes
+      if (lane == 0) s_inv[r] = 1.f;
+      for (int c = lane * 4; c < p.dn; c += 128) {
+        *reinterpret_cast<uint2*>(sNh + r * pnh + c) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(sNl + r * pnh + c) = make_uint2(0u, 0u);
+      }
+      for (int c = lane * 4; c < p.ds; c += 128) {
+        *reinterpret_cast<uint2*>(sSh + r * psh + c) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(sSl + r * psh + c) = make_uint2(0u, 0u);
       }
     } else {
-      if (F16 && lane == 0) s_inv[r] = 1.f;
       for (int c = lane * 4; c < p.dn; c += 128) *reinterpret_cast<float4*>(sN + r * pn + c) = make_float4(0, 0, 0, 0);
       for (int c = lane * 4; c < p.ds; c += 128) *reinterpret_cast<float4*>(sS + r * ps + c) = make_float4(0, 0, 0, 0);
     }
@@ -539,20 +608,18 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
 #pragma unroll
       for (int n = 0; n < NT; ++n) b[n] = __ldg(src + (size_t)n * 32);
     };
+    const int lrow = lane & 15, lk = (lane >> 4) * 8;  // this lane's ldmatrix row / k-half
     auto kstep = [&](int ks, const float4 (&b)[NT]) {
-      const float* tile = ks < ks16_self ? sS : sN;
-      const int pitch = ks < ks16_self ? ps : pn;
-      const int kc = (ks < ks16_self ? ks : ks - ks16_self) * 16 + 2 * tig;
+      const bool self = ks < ks16_self;
+      const int pitch = self ? psh : pnh;
+      const int off = lrow * pitch + (self ? ks : ks - ks16_self) * 16 + lk;
+      const __half* th = (self ? sSh : sNh) + off;
+      const __half* tl = (self ? sSl : sNl) + off;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const float* a = tile + (m * 16 + g) * pitch + kc;
-        const float2 x0 = *reinterpret_cast<const float2*>(a), x1 = *reinterpret_cast<const float2*>(a + 8 * pitch);
-        const float2 x2 = *reinterpret_cast<const float2*>(a + 8), x3 = *reinterpret_cast<const float2*>(a + 8 * pitch + 8);
         uint32_t ah[4], al[4];
-        split_f16x2(x0.x, x0.y, ah[0], al[0]);
-        split_f16x2(x1.x, x1.y, ah[1], al[1]);
-        split_f16x2(x2.x, x2.y, ah[2], al[2]);
-        split_f16x2(x3.x, x3.y, ah[3], al[3]);
+        ldmatrix_x4(ah, th + m * 16 * pitch);
+        ldmatrix_x4(al, tl + m * 16 * pitch);
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
           const uint32_t bh0 = __float_as_uint(b[n].x), bh1 = __float_as_uint(b[n].y);
