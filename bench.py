@@ -49,7 +49,7 @@ REV_ETYPES = {'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by', 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 DRAM_TRAFFIC = {
     ('c2', 'score'): 3.50e9,       # score_topk_kernel<2,2>: 3.31 GB read + 0.19 GB written (profiles/r01_ncu_summary_final.md)
-    ('c2', 'aggregate'): 24.53e9,  # the 4 fused relation kernels + their hub-row kernels of one step (profiles/r01_agg_traffic_c2.csv)
+    ('c2', 'aggregate'): 24.9e9,   # 4 fused relation kernels 13.5 GB + their hub-row kernels 11.4 GB (profiles/r01_ncu_summary_final.md)
 }
 
 
