@@ -5,11 +5,12 @@
 // and the per-destination-type stack+sum/mean/max across relations.
 //
 // Layout: int32 CSR over destination rows; fp32 row-major feature tables. One warp gathers one destination row:
-// 32 lanes x float4 = 512 B per neighbour row (128 columns; two float4 per lane for 256 columns), 8 independent
-// 128-bit loads in flight per lane. A CTA owns a tile of R destination rows: gathered means / maxima and the self
-// rows are staged in shared memory, then the tile is pushed through z = relu(S.Ws^T + N.Wn^T) with a
-// register-blocked FFMA micro-kernel (weights k-major, read through L1), L2-normalised per row and combined into
-// `out` (store / add / max) -- h_neigh never makes a round trip through HBM.
+// 32 lanes x float4 = 512 B per neighbour row (128 columns; two float4 per lane for 256 columns), neighbours taken in
+// groups of exactly 8 / 4 / 2 / 1 independent 128-bit loads, summed with packed add.rn.f32x2. A group of four warps owns
+// a tile of R destination rows: the reduced neighbour rows and the self rows are staged in shared memory (fp16 hi / lo
+// planes, split once by the gathering warp), then the tile is pushed through z = relu(S.Ws^T + N.Wn^T) on the tensor
+// cores (3-product hi/lo split mma.sync, fp32 accurate; A fragments by ldmatrix, pre-packed B fragments from L2),
+// L2-normalised per row and combined into `out` (store / add / max) -- h_neigh never makes a round trip through HBM.
 //
 // Hub rows (> GR_SAGE_LONG_ROW in-edges) are cut into GR_SAGE_CHUNK-edge chunks that are reduced by separate CTAs
 // and summed per row in chunk order, so the result is deterministic and no CTA serialises a 10^6-edge row.
