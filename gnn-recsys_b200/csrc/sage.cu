@@ -390,7 +390,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ ws_t, const float*
 // scaled by a power of two that brings its largest |value| (self and neighbour part together) into [1, 2), and the
 // weights by one global power of two; both are exact, cancel in the L2 normalisation and are divided out otherwise.
 // Error: <= 2^-25 absolute per scaled element (lo halves go subnormal), ~0.5 % of the rtol 1e-4 / atol 1e-5 budget,
-// independent of the input scale (tools/exp_split_f16.py).
+// independent of the input scale (tests/experiments/exp_split_f16.py).
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
   const float2 hf = __half22float2(h);

@@ -89,9 +89,6 @@ class _FrontierSampler:
     def __init__(self, num_layers: int):
         self.num_layers = num_layers
 
-    def _pick(self, layer: int, n_slots_per_row: np.ndarray, rng) -> Optional[np.ndarray]:
-        return None  # None = keep every slot (full neighbourhood)
-
     def frontier(self, g: HeteroGraph, seeds: Dict[str, np.ndarray], layer: int, key: int, exclude=None):
         """Per canonical etype: (src ids, dst ids, edge ids) of the chosen in-edges, edge-id order."""
         out = {}

@@ -11,7 +11,7 @@ CSR over destination rows** -- the layout the CUDA gather-reduce kernel reads.
 Layout rules (same as ``dgl.heterograph``): node types sorted, canonical etypes sorted as tuples,
 edge id = position in the input list, ``num_nodes`` = max id + 1 unless given explicitly.
 CSR construction is a *stable* sort of the edge list by destination id, so neighbours of a row stay
-in edge-id order; it is bit-exact against ``oracle.straightline.csr_by_dst`` (tests/test_graph.py).
+in edge-id order; it is bit-exact against the CPU oracle's restatement (tests/test_host.py).
 """
 from __future__ import annotations
 

@@ -1,5 +1,5 @@
 import sys, numpy as np, torch
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import gnn_recsys_b200 as grb
 from oracle import straightline as O
 torch.manual_seed(1)
