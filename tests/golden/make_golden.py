@@ -133,7 +133,7 @@ def embedding_case(name, n_users, n_items, n_edges, seed, n_layers, hidden, out,
     return d, g, model
 
 
-def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, batch, neg_k, aggregator='mean'):
+def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, batch, neg_k, aggregator='mean', full=False):
     """Config-4 style training-step forward: sampled blocks + positive/negative edge scoring + loss."""
     d = tiny_data(n_users, n_items, n_edges, seed)
     g, _ = shim_graph(d)
@@ -143,7 +143,7 @@ def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, ba
     model = ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, aggregator,
                       'cos', 'sum', True)
     model.eval()
-    sampler = grb.MultiLayerNeighborSampler(fanouts)
+    sampler = grb.MultiLayerFullNeighborSampler(len(fanouts)) if full else grb.MultiLayerNeighborSampler(fanouts)
     eids = {'buys': np.arange(pg.num_edges('buys')), 'clicks': np.arange(pg.num_edges('clicks'))}
     loader = grb.EdgeDataLoader(pg, eids, sampler, exclude='reverse_types',
                                 reverse_etypes={'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by',
@@ -296,3 +296,15 @@ def sport_case(name, aggregator, seed, n_layers=3, hidden=16, out=8, n_users=50,
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sport':
     sport_case('sport_mean_edge', 'mean_edge', 21)
     sport_case('sport_pool_nn', 'pool_nn', 22)
+
+
+def main_forward_extra():
+    """More training-step forwards (config 4 shape) at dims that take the fused tensor-core ConvLayer kernel on SAMPLED
+    blocks (n_src != n_dst, destination prefix), incl. the full-neighbour sampler and a pool_nn stack with fc_preagg."""
+    forward_case('fwd_fanout_mean_128', 400, 150, 6000, seed=12, hidden=128, out=128, fanouts=[10, 10], batch=128, neg_k=50)
+    forward_case('fwd_full_pool_nn', 300, 120, 5000, seed=13, hidden=128, out=64, fanouts=[0, 0], batch=64, neg_k=20,
+                 aggregator='pool_nn', full=True)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'forward':
+    main_forward_extra()

@@ -188,8 +188,9 @@ def test_three_node_type_schema_matches_reference(grb, name):
     assert float(y['sport'].abs().max()) == 0.0
 
 
-def test_forward_scores_and_loss_match_reference(grb):
-    meta, z = load_case('fwd_fanout_mean')
+@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128', 'fwd_full_pool_nn'])
+def test_forward_scores_and_loss_match_reference(grb, name):
+    meta, z = load_case(name)
     dev = torch.device('cuda:0')
     blocks = []
     for li in range(meta['n_blocks']):

@@ -48,8 +48,9 @@ def test_recs_match_reference(name):
     assert_topk_equivalent(vec, z['recs'], scores, meta['k'])
 
 
-def test_forward_scores_and_loss_match_reference():
-    meta, z = load_case('fwd_fanout_mean')
+@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128', 'fwd_full_pool_nn'])
+def test_forward_scores_and_loss_match_reference(name):
+    meta, z = load_case(name)
     blocks = []
     for li in range(meta['n_blocks']):
         ns = {t: int(z['block%d/nsrc/%s' % (li, t)]) for t in ('user', 'item')}
