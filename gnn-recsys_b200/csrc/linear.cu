@@ -41,6 +41,46 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
   }
 }
 
+// ---- tiny d_in, d_out % 4 == 0 and 256 % (d_out / 4) == 0 (the NodeEmbedding shapes: 2 / 4 -> 64 / 128 / 256): a thread
+// keeps ONE group of 4 output columns for the whole kernel, so its d_in x 4 weights and 4 biases live in registers; per
+// row it reads d_in broadcast inputs, does 4 * d_in FMAs and writes one coalesced 128-bit store. No per-element index
+// division, no weight loads in the loop: the kernel is the output-write stream it should be.
+template <int DIN>
+__global__ void __launch_bounds__(256) linear_small_reg_kernel(const float* __restrict__ x, int64_t n,
+                                                               const float* __restrict__ wt,
+                                                               const float* __restrict__ bias, int d_out, int relu,
+                                                               float* __restrict__ y) {
+  const int cols4 = d_out >> 2;
+  const int rows_per_block = 256 / cols4;
+  const int c = (threadIdx.x % cols4) * 4;
+  const int r_in_block = threadIdx.x / cols4;
+  float4 w[DIN];
+#pragma unroll
+  for (int k = 0; k < DIN; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(wt + (size_t)k * d_out + c));
+  const float4 b = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_block + r_in_block; r < n; r += (int64_t)gridDim.x * rows_per_block) {
+    float a[DIN];
+#pragma unroll
+    for (int k = 0; k < DIN; ++k) a[k] = __ldg(x + r * DIN + k);
+    float4 acc = b;
+#pragma unroll
+    for (int k = 0; k < DIN; ++k) {  // same order as the generic kernel: bias, then k ascending
+      acc.x = fmaf(a[k], w[k].x, acc.x); acc.y = fmaf(a[k], w[k].y, acc.y);
+      acc.z = fmaf(a[k], w[k].z, acc.z); acc.w = fmaf(a[k], w[k].w, acc.w);
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    *reinterpret_cast<float4*>(y + r * d_out + c) = acc;
+  }
+}
+
+template <int DIN>
+void launch_small_reg(const float* x, int64_t n, const float* wt, const float* bias, int d_out, int relu, float* y,
+                      cudaStream_t st) {
+  const int rows_per_block = 256 / (d_out / 4);
+  const int grid = (int)std::min<int64_t>((n + rows_per_block - 1) / rows_per_block, (int64_t)gr::sm_count() * 16);
+  linear_small_reg_kernel<DIN><<<grid, 256, 0, st>>>(x, n, wt, bias, d_out, relu, y);
+}
+
 // ---- general: C[M,N] = A[M,K] . B[K,N]; 128x128 tile, BK = 8, 256 threads x (8x8) outputs ---------------------
 constexpr int BM = 128, BN = 128, BK = 8;
 
@@ -268,7 +308,14 @@ extern "C" int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const floa
   GR_REQUIRE(x && wt && y, GR_E_INVALID, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
-  if (d_in <= 8) {
+  const bool reg_ok = d_out % 4 == 0 && d_out <= 1024 && 256 % (d_out / 4) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0 &&
+                      (bias_or_null == nullptr || (reinterpret_cast<uintptr_t>(bias_or_null) & 15) == 0);
+  if (d_in <= 8 && reg_ok && (d_in == 2 || d_in == 4 || d_in == 8)) {
+    if (d_in == 2) launch_small_reg<2>(x, n, wt, bias_or_null, d_out, relu, y, st);
+    else if (d_in == 4) launch_small_reg<4>(x, n, wt, bias_or_null, d_out, relu, y, st);
+    else launch_small_reg<8>(x, n, wt, bias_or_null, d_out, relu, y, st);
+  } else if (d_in <= 8) {
     const int64_t total = n * ((d_out + 3) / 4);
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)gr::sm_count() * 16);
     linear_small_kernel<<<grid, 256, 0, st>>>(x, n, d_in, wt, bias_or_null, d_out, relu, y);
