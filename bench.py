@@ -46,11 +46,17 @@ C4_BATCH, C4_FANOUTS, C4_DELTA = 1024, [10, 10], 0.266
 REV_ETYPES = {'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by', 'clicked-by': 'clicks'}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-DRAM_TRAFFIC = {
-    ('c2', 'score'): 3.50e9,       # score_topk_kernel<2,2>: 3.31 GB read + 0.19 GB written (profiles/r01_ncu_summary_final.md)
-    ('c2', 'aggregate'): 24.9e9,   # 4 fused relation kernels 13.5 GB + their hub-row kernels 11.4 GB (profiles/r01_ncu_summary_final.md)
-}
+def dram_traffic(config, stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step of one stage's kernels, from the committed ncu capture of
+    THIS round's kernels: profiles/traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` raw CSV.
+    None when no capture of the current kernels exists for the config (never a stale constant)."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(config, {}).get(stage)
+    return None if e is None else e.get('dram_bytes')
 
 
 def peaks():
@@ -351,9 +357,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(WORKLOADS))
-    ap.add_argument('--elem', default='bf16', choices=['bf16', 'fp16'])
-    ap.add_argument('--parts', type=int, default=2, choices=[1, 2])
-    ap.add_argument('--shortlist', type=int, default=16)
+    ap.add_argument('--elem', default='fp16', choices=['bf16', 'fp16'])
+    ap.add_argument('--parts', type=int, default=None, choices=[1, 2], help='shorthand: 1 = single product, 2 = 3-product hi/lo split without a second pass')
+    ap.add_argument('--parts-users', type=int, default=1, choices=[1, 2])
+    ap.add_argument('--parts-items', type=int, default=1, choices=[1, 2])
+    ap.add_argument('--shortlist', type=int, default=32)
+    ap.add_argument('--no-k-band', action='store_true')
     ap.add_argument('--item-shards', type=int, default=None, help='N>1 scoring layout: N = item-range shards + owner-side top-k merge; 1 = user-range shards, replicated item table; default: shard the longer side')
     ap.add_argument('--neg-k', type=int, default=2500, help='c4: negatives per positive edge (reference default 2500)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -406,7 +415,8 @@ def main():
     buys = data.relations()[('user', 'buys', 'item')]
     bought = grb.BoughtCSR.from_edges(buys[0], buys[1], n_users)
     bought.on(dev)
-    cfg = grb.RecsConfig(elem=args.elem, parts=args.parts, shortlist=args.shortlist)
+    cfg = grb.RecsConfig(elem=args.elem, parts=args.parts, parts_users=args.parts_users, parts_items=args.parts_items,
+                         shortlist=args.shortlist, k_band=not args.no_k_band)
     feats_dev = {t: g.nodes[t].data['features'].to(dev) for t in g.ntypes}
     uid_all = np.arange(n_users)
 
@@ -441,7 +451,7 @@ def main():
             mark('prep0')
             ids, scores, owned = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark, item_shards=args.item_shards)
             own_range[0] = owned
-            n_over = torch.zeros(1, dtype=torch.int32, device=dev)
+            n_over = (0, 0)
         mark('t1')
         if record is not None:
             record.append(ev)
@@ -523,6 +533,7 @@ def main():
         return float(np.mean([e[a].elapsed_time(e[b]) for e in rec if a in e and b in e])) if rec and a in rec[0] and b in rec[0] else None
     stages = {'embed_in_ms': stage_ms('t0', 'embed_in'), 'aggregate_ms': stage_ms('embed_in', 'aggregate'),
               'prep_ms': stage_ms('aggregate', 'score_begin'), 'score_ms': stage_ms('score_begin', 'score_end'),
+              'rescore_ms': stage_ms('score_end', 'rescore_end'), 'second_pass_ms': stage_ms('rescore_end', 'fallback_end'),
               'rescore_merge_ms': stage_ms('score_end', 't1')}
     if world > 1:
         stages['note'] = ('rank 0; aggregate_ms includes the per-layer NCCL all-gather, '
@@ -561,7 +572,7 @@ def main():
         gbs = agg_bytes / world / (stages['aggregate_ms'] * 1e-3) / 1e9
         shard_note = '' if world == 1 else ", this rank's 1/%d of the rows, all-gather time included" % world
         roof_agg = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm'],
-                    'traffic': DRAM_TRAFFIC.get((args.config, 'aggregate')) if world == 1 else None,
+                    'traffic': dram_traffic(args.config, 'aggregate') if world == 1 else None,
                     'algorithmic_bytes': agg_bytes // world, 'of': pk['source'], 'per': 'GPU',
                     'note': 'all fused CSR gather-reduce + projection kernels of one step (4 relations%s); '
                             'bytes = SURVEY 8d B_dst' % shard_note}
@@ -570,10 +581,13 @@ def main():
     if stages.get('score_ms'):
         tf = flops / world / (stages['score_ms'] * 1e-3) / 1e12
         roof = {'bound': 'tensor', 'achieved': tf, 'peak': pk['tc'], 'unit': 'TFLOP/s', 'frac': tf / pk['tc'],
-                'traffic': DRAM_TRAFFIC.get((args.config, 'score')) if world == 1 else None, 'per': 'GPU', 'executed_tflops': tf * (3 if args.parts == 2 else 1),
-                'executed_frac': tf * (3 if args.parts == 2 else 1) / pk['tc'], 'of': pk['source'] + ' (sustained)',
-                'kernel': 'score_topk_kernel (tcgen05 %s, %d-product, fused top-%d shortlist)' % (args.elem, 3 if args.parts == 2 else 1, args.shortlist),
-                'note': 'achieved counts 2*U*I*D once; the %d-product split executes %dx that on the tensor pipe' % (3 if args.parts == 2 else 1, 3 if args.parts == 2 else 1)}
+                'traffic': dram_traffic(args.config, 'score') if world == 1 else None, 'per': 'GPU',
+                'executed_tflops': tf * cfg.products, 'executed_frac': tf * cfg.products / pk['tc'],
+                'of': pk['source'] + ' (sustained)',
+                'kernel': 'score_topk_kernel (tcgen05 kind::f16 %s, %d-product first pass, fused top-%d shortlist)' % (args.elem, cfg.products, args.shortlist),
+                'note': 'achieved counts 2*U*I*D once over the first-pass kernel time (score_ms); that pass executes %dx of '
+                        'it on the tensor pipe; users it cannot prove (overflow_users[0]) go through the %s second pass, '
+                        'timed in second_pass_ms' % (cfg.products, '3-product' if cfg.second else 'exact fp32')}
     elif roof_agg is not None:
         roof = roof_agg
 
@@ -584,12 +598,12 @@ def main():
     line = {
         'metric': 'users/sec for full-graph embed+top-10 recs', 'value': value, 'unit': 'users/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 embeddings + %s%s scoring (f32 accumulate, f32 re-score)' % (args.elem, 'x3' if args.parts == 2 else ''),
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 embeddings + %s x%d-product tcgen05 scoring (f32 accumulate, exact f32 re-score + proof%s)' % (args.elem, cfg.products, ', 3-product second pass' if cfg.second else ''),
         'data': 'synthetic', 'config': workload_config(args.config, wl, world, args.item_shards),
         'e2e': {'value': n_users / e2e_s, 'unit': 'users/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_aggregation': roof_agg,
-        'cpu_baseline': cpu, 'stages_ms': stages, 'overflow_users': int(n_over.item()), 'verified_vs_exact_fp32': verified,
+        'cpu_baseline': cpu, 'stages_ms': stages, 'overflow_users': list(n_over), 'verified_vs_exact_fp32': verified,
         'setup_s': {'generate': t_gen, 'ingest_csr_build': t_ingest},
     }
     print(json.dumps(line))

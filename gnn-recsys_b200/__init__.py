@@ -13,4 +13,4 @@ from .train.run import get_embeddings  # noqa: F401
 from .metrics import (get_recs, get_recs_tensor, create_already_bought, create_already_bought_csr,  # noqa: F401
                       create_ground_truth, recs_to_metrics, get_metrics_at_k, metrics_from_tensor)
 from .recs import RecsConfig, BoughtCSR, ScoringTable, recommend_topk  # noqa: F401
-from . import ops, _native, distributed  # noqa: F401
+from . import ops, _native, distributed, recs  # noqa: F401

@@ -20,6 +20,7 @@ REDUCE_MEAN, REDUCE_MAX = 0, 1
 ACC_STORE, ACC_ADD, ACC_MAX = 0, 1, 2
 ELEM_BF16, ELEM_FP16 = 0, 1
 SCORE_MAX_SPLITS = 32
+SCORE_FLAG_SINGLE_CTA = 1
 
 _i32, _i64, _f32, _sz, _vp = C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_void_p
 
@@ -41,12 +42,12 @@ SIGNATURES = {
     'gr_colmean_normalized_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
     'gr_score_prep': (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     'gr_score_splits': (C.c_int, [_i64, _i64]),
-    'gr_score_pair_mode': (C.c_int, [C.c_int]),
     'gr_score_topk_workspace_bytes': (_sz, [_i64, _i64, _i32]),
-    'gr_score_topk_tc': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _sz,
-                                   _vp]),
-    'gr_rescore_topk_f32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _vp, _f32, _f32, _f32, _i32,
-                                      _f32, _vp, _vp, _vp, _vp, _vp]),
+    'gr_score_topk_tc': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp,
+                                   _i32, _vp, _vp, _vp, _sz, _vp]),
+    'gr_score_band': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp]),
+    'gr_rescore_topk_f32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _f32, _vp,
+                                      _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gr_score_topk_exact_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _f32, _vp, _f32,
                                           _vp, _vp, _vp]),
     'gr_metrics_workspace_bytes': (_sz, [_i64]),

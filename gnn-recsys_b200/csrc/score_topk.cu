@@ -1,32 +1,37 @@
-// gr_score_topk_tc: all-users x all-items scoring with a fused running top-S shortlist (stage 1 of get_recs).
+// gr_score_topk_tc: all-users x all-items scoring with a fused running shortlist (stage 1 of get_recs).
 //
 // Replaces the reference's per-user loop (src/metrics.py:52-77): torch.cat repeat of the user row, one
 // nn.CosineSimilarity call over all items, a D2H copy of I scores, np.argsort and a Python already-bought filter --
 // with ONE dense contraction users[U, D] x items[I, D]^T on the 5th-generation tensor cores:
 //
-//   * operands: 16-bit (bf16 or fp16), K-major, 128-byte-swizzled shared-memory tiles written by TMA
-//     (cp.async.bulk.tensor). With parts == 2 every row carries a hi and a lo half (x = hi + lo up to 2^-18 / 2^-22
-//     relative) and the score is the 3-product sum hi.hi + lo.hi + hi.lo, all accumulated in the same TMEM tile,
-//     which brings the 16-bit rounding error down to the 1e-5 tie tolerance of the parity contract.
-//   * math: tcgen05.mma.cta_group::1.kind::f16, M = 128 users x N = 128 items x K = 16, fp32 accumulators in TMEM
-//   * a CTA owns 256 users (two 128-row A tiles, resident in shared memory for the whole sweep) and walks its item
-//     range once. B arrives in 32 KB chunks (one part of one 128-item tile) through a TMA ring; every chunk feeds
-//     both user tiles, halving the L2 traffic per FLOP. The four 128-column accumulators ([user tile] x [double
-//     buffer]) fill all 512 TMEM columns, so the epilogue of tile j overlaps the MMAs of tile j+1.
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 = epilogue. An epilogue
-//     thread owns ONE user row (TMEM lane) for the whole sweep: tcgen05.ld 32 scores at a time, a 3-input max tree
-//     (FMNMX3) and one compare against the row's running threshold (~0.55 instructions per score); only scores that
-//     beat the threshold take the slow path: already-bought test against the user's sorted id list (a cached "next
-//     bought id" makes the common case one compare) and insertion into the row's sorted shortlist (global memory,
-//     thread-private, L1-resident).
-//   * scores are never materialised (10M x 1M would be 40 TB); the shortlist is re-scored exactly in fp32 by
-//     gr_rescore_topk_f32, which also proves that it contains the exact top-k.
+//   * operands: 16-bit (fp16 or bf16), K-major, 128-byte-swizzled shared-memory tiles written by TMA
+//     (cp.async.bulk.tensor). Each side carries 1 or 2 parts per row (hi, or hi + lo with x = hi + lo up to 2^-22 /
+//     2^-18 relative); the product scheme follows from (parts_users, parts_items):
+//       (1, 1)  hi.hi                    1 product   -- the default first pass (fp16, shortlist 32)
+//       (2, 1)  hi.hi + lo.hi            2 products  -- user row exact, item row rounded once
+//       (2, 2)  hi.hi + lo.hi + hi.lo    3 products  -- fp32-grade, the second pass for users the first cannot prove
+//     all accumulated in the same TMEM tile. Whatever the scheme, the ANSWER comes from gr_rescore_topk_f32, which
+//     re-scores the shortlist in exact fp32 and proves per user that nothing outside it can reach the top-k.
+//   * math: tcgen05.mma.cta_group::2.kind::f16, M = 256 users (128 from each CTA of a pair) x N = 128 items x K = 16,
+//     fp32 accumulators in TMEM. A CTA owns 256 users (two 128-row A tiles per part, resident in shared memory for the
+//     whole sweep) and walks its item range once; of every 128-item B sub-tile (64 K-elements of one part) a CTA
+//     TMA-loads and holds only ITS 64 rows (8 KB slots in a ring). The four 128-column accumulators ([user tile] x
+//     [double buffer]) fill all 512 TMEM columns, so the epilogue of tile j overlaps the MMAs of tile j + 1.
+//     A single-CTA variant (cta_group::1) is kept behind GR_SCORE_FLAG_SINGLE_CTA and for d_pad = 64.
+//   * warp roles (352 threads): warp 0 = TMA producer; warps 1 and 10 = MMA issuers, one per user tile (+ TMEM
+//     alloc); warps 2-9 = epilogue. An epilogue thread owns ONE user row (TMEM lane) for the whole sweep: four
+//     tcgen05.ld.32x32b.x32 drain the row's 128 scores into registers, the TMEM slot is released immediately, then a
+//     3-input max tree (FMNMX3) and one compare per 32 scores against the row's running threshold. Only scores that
+//     beat it take the (compact, out-of-line) slow path: already-bought test against the user's sorted id list and
+//     insertion into the row's sorted shortlist ([S][256] in shared memory).
+//   * threshold: tau = max(S-th best so far, k-th best so far - band). The second term drops candidates that can
+//     no longer reach the exact top-k (band >= 2 x the approximation error, a device scalar written by the host side
+//     from the operand statistics), which halves the slow-path traffic of a 32-entry shortlist; the re-score kernel
+//     accounts for both kinds of dropped items in its proof.
+//   * scores are never materialised (10M x 1M would be 40 TB).
 //   * small user counts: the item range is split over blockIdx.y so the grid still fills the chip; the per-split
 //     shortlists are merged by gr_topk_merge (host side of this file).
 #include <cuda.h>
-#include <stdlib.h>
-
-#include <atomic>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -180,47 +185,54 @@ __device__ __forceinline__ uint32_t select_n(const uint32_t* v, int i) {
 __device__ __forceinline__ uint32_t select32(const uint32_t* v, int i) { return select_n<32>(v, i); }
 
 // ---- slow path -------------------------------------------------------------------------------------------------
-// Candidate `s` (item `gid`) beat the threshold of CTA row `t`. The row's shortlist is column t of ls / li
-// ([S][256] in shared memory, scores descending). s_nb[t] caches the smallest already-bought id >= the last id
-// looked up, so the common case of the bought test is one compare. Returns the new threshold (S-th best so far).
-__device__ __noinline__ float shortlist_insert(float s, int gid, int t, int S, float* __restrict__ ls,
-                                               int* __restrict__ li, int* __restrict__ s_nb, long long b0,
-                                               long long b1, const int* __restrict__ bought_ids) {
-  if (gid >= s_nb[t]) {  // may be an already-bought item: first bought id >= gid
-    long long lo = b0, hi = b1;
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (bought_ids[mid] < gid) lo = mid + 1; else hi = mid;
-    }
-    const bool is_bought = lo < b1 && bought_ids[lo] == gid;
-    long long nxt = lo;
-    if (is_bought)  // skip duplicates of the same id (multi-edges)
-      while (nxt < b1 && bought_ids[nxt] == gid) ++nxt;
-    s_nb[t] = nxt < b1 ? bought_ids[nxt] : 0x7fffffff;
-    if (is_bought) return ls[(S - 1) * ROWS_PER_CTA + t];
-  }
-  int lo = 0, hi = S - 1;  // first position whose score is < s (equal scores keep the earlier, smaller id first)
+// Shortlists live in shared memory ROW-major: row t of the CTA owns ls / li [t * lst .. t * lst + S), lst = S | 1 (odd
+// pitch: conflict-free both for a thread walking its own row and for a warp reading one row with one entry per lane).
+//
+// bought_test: is `gid` one of row t's already-bought items? s_nb[t] caches the smallest bought id >= the last id looked
+// up, so the common case is one compare (ids arrive in ascending order).
+__device__ __noinline__ bool bought_test(int gid, int t, int* __restrict__ s_nb, long long b0, long long b1,
+                                         const int* __restrict__ bought_ids) {
+  if (gid < s_nb[t]) return false;
+  long long lo = b0, hi = b1;  // first bought id >= gid
   while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (ls[mid * ROWS_PER_CTA + t] >= s) lo = mid + 1; else hi = mid;
+    const long long mid = (lo + hi) >> 1;
+    if (bought_ids[mid] < gid) lo = mid + 1; else hi = mid;
   }
-  for (int j = S - 1; j > lo; --j) {
-    ls[j * ROWS_PER_CTA + t] = ls[(j - 1) * ROWS_PER_CTA + t];
-    li[j * ROWS_PER_CTA + t] = li[(j - 1) * ROWS_PER_CTA + t];
-  }
-  ls[lo * ROWS_PER_CTA + t] = s;
-  li[lo * ROWS_PER_CTA + t] = gid;
-  return ls[(S - 1) * ROWS_PER_CTA + t];
+  const bool is_bought = lo < b1 && bought_ids[lo] == gid;
+  long long nxt = lo;
+  if (is_bought)  // skip duplicates of the same id (multi-edges)
+    while (nxt < b1 && bought_ids[nxt] == gid) ++nxt;
+  s_nb[t] = nxt < b1 ? bought_ids[nxt] : 0x7fffffff;
+  return is_bought;
 }
 
-// Shared-memory plan: [A: UT x PARTS x KB sub-tiles][B ring: `ring` sub-tiles of 16 KB][shortlists][next-bought][barriers]
+// Warp-cooperative sorted insert of candidate (s, gid) into ONE row's shortlist (rl / ri, scores descending): lane j
+// holds entry j, a ballot finds the insert position, one shuffle shifts the tail, every lane stores its own slot -- a
+// dozen instructions, no divergence and no dependent shared-memory chain (the per-thread shift loop this replaces cost
+// ~1000 cycles per insert and stalled the whole warp). Equal scores keep the earlier (smaller) id first. Lane j only
+// ever touches slot j, so back-to-back inserts need no barrier. Returns the row's new threshold
+// max(S-th best, k-th best - band) in every lane.
+__device__ __noinline__ float coop_insert(float s, int gid, float* __restrict__ rl, int* __restrict__ ri, int S, int kk,
+                                          float band, int lane) {
+  const float e = lane < S ? rl[lane] : -INFINITY;
+  const int ei = lane < S ? ri[lane] : -1;
+  const int pos = __popc(__ballot_sync(0xffffffffu, e >= s));  // sorted descending: the lanes with e >= s are a prefix
+  const float up = __shfl_up_sync(0xffffffffu, e, 1);
+  const int upi = __shfl_up_sync(0xffffffffu, ei, 1);
+  const float ne = lane < pos ? e : (lane == pos ? s : up);
+  const int nei = lane < pos ? ei : (lane == pos ? gid : upi);
+  if (lane >= pos && lane < S) { rl[lane] = ne; ri[lane] = nei; }
+  return fmaxf(__shfl_sync(0xffffffffu, ne, S - 1), __shfl_sync(0xffffffffu, ne, kk - 1) - band);
+}
+
+// Shared-memory plan: [A: UT x PA x KB sub-tiles][B ring: `ring` slots][shortlists][next-bought][barriers]
 constexpr int MAX_RING = 8;
-template <int KB, int PARTS, bool PAIR = false>
+template <int KB, int PA, bool PAIR = false>
 struct Cfg {
-  static constexpr int A_BYTES = UT * PARTS * KB * SUB_BYTES;
+  static constexpr int A_BYTES = UT * PA * KB * SUB_BYTES;
   static constexpr int SLOT_BYTES = PAIR ? SUB_BYTES / 2 : SUB_BYTES;  // a CTA of a pair holds half of every B sub-tile
   static constexpr int TAIL_BYTES = ROWS_PER_CTA * 4 + 512;  // s_nb + barriers
-  static int list_bytes(int S) { return S * ROWS_PER_CTA * 8; }
+  static int list_bytes(int S) { return (S | 1) * ROWS_PER_CTA * 8; }  // row pitch S | 1
   static int ring(int S) {
     const int r = (SMEM_LIMIT - 1024 - A_BYTES - list_bytes(S) - TAIL_BYTES) / SLOT_BYTES;
     return r > MAX_RING ? MAX_RING : r;
@@ -228,19 +240,20 @@ struct Cfg {
   static size_t smem(int S) { return 1024 /*alignment slack*/ + A_BYTES + (size_t)ring(S) * SLOT_BYTES + list_bytes(S) + TAIL_BYTES; }
 };
 
-// MODE (debug / profiling only, see DESIGN.md "pipeline experiments"): 0 = product kernel; 1 = epilogue reads TMEM but
-// skips the top-k scan; 2 = epilogue releases the accumulator without reading it; 3 = MMA warp commits without MMAs.
+// PA / PB: parts per user / item row (1 = hi, 2 = hi + lo). Item part 0 (hi) pairs with every user part, item part 1
+// (lo) with the user hi part only: (1,1) hi.hi; (2,1) hi.hi + lo.hi; (2,2) hi.hi + lo.hi + hi.lo.
 // PAIR: two CTAs of a cluster work as one cta_group::2 unit -- M = 256 MMAs (128 user rows from each CTA), each CTA
 // TMA-loads and holds only HALF of every item sub-tile (64 rows), so the shared-memory and L2 traffic per FLOP halve.
 // The even CTA (leader) issues every MMA; TMA completions of both CTAs land on the leader's barriers, MMA commits
 // are multicast to both CTAs, epilogues of both CTAs release the accumulators on the leader's barriers.
-template <int KB, int PARTS, int MODE, bool PAIR>
+template <int KB, int PA, int PB, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_constant__ CUtensorMap tm_items,
                   long long n_users, long long n_items, long long item_id_base, int tiles_per_split, uint32_t idesc,
-                  const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int ring,
+                  const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int kk,
+                  const float* __restrict__ band_ptr, const int* __restrict__ user_map, int ring,
                   float* __restrict__ sl_score, int* __restrict__ sl_id) {
-  using L = Cfg<KB, PARTS, PAIR>;
+  using L = Cfg<KB, PA, PAIR>;
   constexpr int D_PAD = KB * KBLK;
   constexpr int SLOT = L::SLOT_BYTES;
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
@@ -249,9 +262,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
   uint8_t* sB = sA + L::A_BYTES;
-  float* ls = reinterpret_cast<float*>(sB + ring * SLOT);  // [S][256]
-  int* li = reinterpret_cast<int*>(ls + S * ROWS_PER_CTA);       // [S][256]
-  int* s_nb = li + S * ROWS_PER_CTA;                              // [256]
+  const int lst = S | 1;                                          // shortlist row pitch
+  float* ls = reinterpret_cast<float*>(sB + ring * SLOT);  // [256][lst]
+  int* li = reinterpret_cast<int*>(ls + lst * ROWS_PER_CTA);     // [256][lst]
+  int* s_nb = li + lst * ROWS_PER_CTA;                            // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_nb + ROWS_PER_CTA);
   uint64_t* full = bars;                  // [MAX_RING]  TMA -> MMA
   uint64_t* empty = full + MAX_RING;      // [MAX_RING]  MMA -> TMA
@@ -288,20 +302,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer: one 16 KB sub-tile (64 K-elements of one part of one item tile) per ring slot
+    // ================= TMA producer: one sub-tile (64 K-elements of one part of one item tile) per ring slot
     if (lane == 0 && n_tiles > 0) {
       if (leader) mbar_expect_tx(a_full, (PAIR ? 2 : 1) * L::A_BYTES);
       for (int ut = 0; ut < UT; ++ut)
-        for (int pa = 0; pa < PARTS; ++pa)
+        for (int pa = 0; pa < PA; ++pa)
           for (int kb = 0; kb < KB; ++kb) {
-            void* dst = sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES;
+            void* dst = sA + ((ut * PA + pa) * KB + kb) * SUB_BYTES;
             if (PAIR) tma_load_2d_pair(dst, &tm_users, pa * D_PAD + kb * KBLK, (int)(row_base + ut * TILE_M), a_full);
             else tma_load_2d(dst, &tm_users, pa * D_PAD + kb * KBLK, (int)(row_base + ut * TILE_M), a_full);
           }
       int buf = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
-        for (int pb = 0; pb < PARTS; ++pb) {
+        for (int pb = 0; pb < PB; ++pb) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(empty + buf, phase ^ 1u);
             if (PAIR) {  // this CTA's 64 rows of the 128-item sub-tile; the bytes of both halves count on the leader
@@ -318,8 +332,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       }
     }
   } else if (warp == 1 || warp == MMA_WARP1) {
-    // ================= MMA issuers: one thread per user tile (a single thread cannot issue 48 MMAs per item tile
-    // fast enough to keep the tensor pipe busy: ~13 SASS instructions of descriptor traffic per MMA) =================
+    // ================= MMA issuers: one thread per user tile (a single thread cannot issue the MMAs of both user
+    // tiles fast enough to keep the tensor pipe busy: ~13 SASS instructions of descriptor traffic per MMA) ===========
     const int ut = warp == 1 ? 0 : 1;
     if (lane == 0 && n_tiles > 0 && leader) {
       mbar_wait(a_full, 0);
@@ -329,7 +343,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       for (int j = 0; j < n_tiles; ++j) {
         const int slot = j & 1;
         const uint32_t aphase = (uint32_t)(j >> 1) & 1u;
-        for (int pb = 0; pb < PARTS; ++pb) {
+        for (int pb = 0; pb < PB; ++pb) {
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(full + buf, phase);
@@ -341,20 +355,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
                 mbar_wait(t_empty + ut * 2 + slot, aphase ^ 1u);
                 tc_fence_after();
               }
-              // B part 0 (hi) pairs with every A part; B part 1 (lo) pairs with A hi only: hi.hi + lo.hi + hi.lo
-              const int n_pa = pb == 0 ? PARTS : 1;
+              const int n_pa = pb == 0 ? PA : 1;
               for (int pa = 0; pa < n_pa; ++pa) {
-                const uint64_t da = make_desc_sw128(smem_u32(sA + ((ut * PARTS + pa) * KB + kb) * SUB_BYTES));
+                const uint64_t da = make_desc_sw128(smem_u32(sA + ((ut * PA + pa) * KB + kb) * SUB_BYTES));
 #pragma unroll
-                for (int k = 0; k < KBLK / UMMA_K; ++k)  // +32 bytes (>>4 = 2) per K = 16 step inside the swizzle atom
-                  if (MODE != 3) {
-                    if (PAIR) tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                              (pb | kb | pa | k) != 0 ? 1u : 0u);
-                    else tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                    (pb | kb | pa | k) != 0 ? 1u : 0u);
-                  }
+                for (int k = 0; k < KBLK / UMMA_K; ++k) {  // +32 bytes (>>4 = 2) per K = 16 step inside the swizzle atom
+                  if (PAIR) tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                            (pb | kb | pa | k) != 0 ? 1u : 0u);
+                  else tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (pb | kb | pa | k) != 0 ? 1u : 0u);
+                }
               }
-              if (pb == PARTS - 1 && kb == KB - 1) {
+              if (pb == PB - 1 && kb == KB - 1) {
                 if (PAIR) tc_commit_pair(t_full + ut * 2 + slot); else tc_commit(t_full + ut * 2 + slot);
               }
             }
@@ -372,9 +384,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
     const int t = ut * TILE_M + q * 32 + lane;
     const long long row = row_base + t;
     const bool live = row < n_users;
-    for (int s = 0; s < S; ++s) { ls[s * ROWS_PER_CTA + t] = -INFINITY; li[s * ROWS_PER_CTA + t] = -1; }
+    const float band = band_ptr != nullptr ? __ldg(band_ptr) : INFINITY;  // +inf: plain S-th-best threshold
+    const int t0 = t - lane;  // first CTA row of this warp
+    for (int s = 0; s < S; ++s) { ls[t * lst + s] = -INFINITY; li[t * lst + s] = -1; }
     long long b0 = 0, b1 = 0;
-    if (live && bought_indptr != nullptr) { b0 = bought_indptr[row]; b1 = bought_indptr[row + 1]; }
+    if (live && bought_indptr != nullptr) {  // bought lists are indexed by the ORIGINAL user row
+      const long long brow = user_map != nullptr ? (long long)user_map[row] : row;
+      b0 = bought_indptr[brow]; b1 = bought_indptr[brow + 1];
+    }
     {
       long long lo = b0, hi = b1;  // first bought id >= first item id of this CTA's range
       const long long first_id = item_id_base + (long long)tile0 * TILE_N;
@@ -397,20 +414,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       // drain the whole accumulator row into registers, then hand the TMEM slot straight back to the MMA warp:
       // the scan below (and its data-dependent slow path) never holds up the tensor pipe
       uint32_t v[TILE_N];
-      if (MODE != 2) {
 #pragma unroll
-        for (int c = 0; c < TILE_N / 32; ++c) tc_ld32(taddr + (uint32_t)(c * 32), v + c * 32);
-        tc_ld_wait();
-      }
+      for (int c = 0; c < TILE_N / 32; ++c) tc_ld32(taddr + (uint32_t)(c * 32), v + c * 32);
+      tc_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (PAIR) mbar_arrive_leader(t_empty + ut * 2 + slot); else mbar_arrive(t_empty + ut * 2 + slot);
-      }
-      if (MODE == 2) continue;
-      if (MODE == 1) {
-        if (__uint_as_float(v[lane]) == 123456.f) tau = 0.f;  // keep the loads alive
-        continue;
       }
 #pragma unroll
       for (int c = 0; c < TILE_N / 32; ++c) {
@@ -422,28 +432,46 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
         m[10] = fmaxf(__uint_as_float(v[c * 32 + 30]), __uint_as_float(v[c * 32 + 31]));
         const float mx = max3(max3(m[0], m[1], m[2]), max3(m[3], m[4], m[5]),
                               max3(max3(m[6], m[7], m[8]), m[9], m[10]));
-        if (mx > tau) {
-          // Rare after the first tiles, and deliberately COMPACT code (a bit mask + a select tree instead of one call
-          // site per column): the slow path runs cold, so its cost is instruction-cache lines, not instructions.
+        if (__any_sync(0xffffffffu, mx > tau)) {
+          // Slow path, rare after the first tiles and deliberately COMPACT (a bit mask + a select tree instead of one
+          // call site per column: it runs cold, so its cost is instruction-cache lines, not instructions). The whole
+          // warp enters: every lane pops its own next candidate (bought test included), then the pending candidates
+          // are inserted one row at a time by all 32 lanes together.
           const int id0 = (int)(item_id_base + (long long)(tile0 + j) * TILE_N) + c * 32;
           uint32_t cand = 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (__uint_as_float(v[c * 32 + i]) > tau) cand |= 1u << i;
           if (partial) cand &= (id_end - id0 >= 32) ? 0xffffffffu : (id_end > id0 ? (1u << (id_end - id0)) - 1u : 0u);
-          while (cand != 0) {
-            const int i = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const float s = __uint_as_float(select32(v + c * 32, i));
-            if (s > tau) tau = shortlist_insert(s, id0 + i, t, S, ls, li, s_nb, b0, b1, bought_ids);
+          for (;;) {
+            float s = 0.f;
+            int gid = -1;
+            while (cand != 0) {
+              const int i = __ffs(cand) - 1;
+              cand &= cand - 1;
+              const float sv = __uint_as_float(select32(v + c * 32, i));
+              if (sv > tau && !bought_test(id0 + i, t, s_nb, b0, b1, bought_ids)) { s = sv; gid = id0 + i; break; }
+            }
+            uint32_t pend = __ballot_sync(0xffffffffu, gid >= 0);
+            if (pend == 0) break;
+            while (pend != 0) {
+              const int L = __ffs(pend) - 1;
+              pend &= pend - 1;
+              const float nt = coop_insert(__shfl_sync(0xffffffffu, s, L), __shfl_sync(0xffffffffu, gid, L),
+                                           ls + (t0 + L) * lst, li + (t0 + L) * lst, S, kk, band, lane);
+              if (lane == L) tau = nt;
+            }
           }
         }
       }
     }
-    if (live) {  // [split][row][S]
-      float* os = sl_score + ((long long)blockIdx.y * n_users + row) * S;
-      int* oi = sl_id + ((long long)blockIdx.y * n_users + row) * S;
-      for (int s = 0; s < S; ++s) { os[s] = ls[s * ROWS_PER_CTA + t]; oi[s] = li[s * ROWS_PER_CTA + t]; }
+    __syncwarp();
+    for (int L = 0; L < 32; ++L) {  // [split][row][S]: one coalesced row per iteration
+      const long long r = row_base + t0 + L;
+      if (r < n_users && lane < S) {
+        sl_score[((long long)blockIdx.y * n_users + r) * S + lane] = ls[(t0 + L) * lst + lane];
+        sl_id[((long long)blockIdx.y * n_users + r) * S + lane] = li[(t0 + L) * lst + lane];
+      }
     }
   }
   tc_fence_before();
@@ -497,15 +525,17 @@ struct ScoreArgs {
   uint32_t ab_format;
   const long long* bptr;
   const int* bids;
-  int S;
+  int S, k;
+  const float* band;
+  const int* user_map;
   float* sl_score;
   int* sl_id;
 };
 
-template <int KB, int PARTS, int MODE = 0, bool PAIR = false>
+template <int KB, int PA, int PB, bool PAIR>
 int launch_score(const ScoreArgs& a, cudaStream_t st) {
-  auto kern = score_topk_kernel<KB, PARTS, MODE, PAIR>;
-  using L = Cfg<KB, PARTS, PAIR>;
+  auto kern = score_topk_kernel<KB, PA, PB, PAIR>;
+  using L = Cfg<KB, PA, PAIR>;
   const int ring = L::ring(a.S);
   GR_REQUIRE(ring >= 2, GR_E_INVALID, "shortlist too large for the shared-memory budget of this configuration");
   const size_t smem = L::smem(a.S);
@@ -525,22 +555,27 @@ int launch_score(const ScoreArgs& a, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     GR_CUDA(cudaLaunchKernelEx(&cfg, kern, a.mu, a.mi_half, a.n_users, a.n_items, a.item_id_base, a.tiles_per_split,
-                               idesc, a.bptr, a.bids, a.S, ring, a.sl_score, a.sl_id));
+                               idesc, a.bptr, a.bids, a.S, a.k, a.band, a.user_map, ring, a.sl_score, a.sl_id));
   } else {
     kern<<<dim3(gx, (unsigned)a.splits), NUM_THREADS, smem, st>>>(a.mu, a.mi, a.n_users, a.n_items, a.item_id_base,
-                                                                  a.tiles_per_split, idesc, a.bptr, a.bids, a.S, ring,
-                                                                  a.sl_score, a.sl_id);
+                                                                  a.tiles_per_split, idesc, a.bptr, a.bids, a.S, a.k,
+                                                                  a.band, a.user_map, ring, a.sl_score, a.sl_id);
   }
   GR_LAUNCH_CHECK();
   return GR_OK;
+}
+
+template <int KB, bool PAIR>
+int launch_scheme(const ScoreArgs& a, int pa, int pb, cudaStream_t st) {
+  if (pa == 1 && pb == 1) return launch_score<KB, 1, 1, PAIR>(a, st);
+  if (pa == 2 && pb == 1) return launch_score<KB, 2, 1, PAIR>(a, st);
+  return launch_score<KB, 2, 2, PAIR>(a, st);
 }
 
 // item-range splits: enough CTAs for two waves when the user count alone cannot fill the chip. (Splitting further
 // to shorten a nearly empty last wave was measured and rejected: every split restarts its shortlists, and the
 // warm-up insertions cost more than the wave round-up saves -- 250k x 200k: 29.6 ms unsplit, 39.5 ms in 3 splits.)
 int choose_splits(long long n_users, long long n_items) {
-  static const int forced = getenv("GR_SCORE_SPLITS") ? atoi(getenv("GR_SCORE_SPLITS")) : 0;  // experiments only
-  if (forced > 0) return (int)std::min<long long>(forced, std::max<long long>(1, (n_items + TILE_N - 1) / TILE_N));
   long long ctas = (n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
   ctas += ctas & 1;  // CTA pairs
   const long long tiles = (n_items + TILE_N - 1) / TILE_N;
@@ -552,14 +587,6 @@ int choose_splits(long long n_users, long long n_items) {
 }
 
 }  // namespace
-
-// 1 = CTA-pair kernel (default), 0 = single-CTA kernel; GR_SCORE_PAIR in the environment sets the initial value
-static std::atomic<int> g_pair_mode{getenv("GR_SCORE_PAIR") ? atoi(getenv("GR_SCORE_PAIR")) : 1};
-
-extern "C" int gr_score_pair_mode(int set_or_negative) {
-  if (set_or_negative >= 0) g_pair_mode.store(set_or_negative != 0 ? 1 : 0);
-  return g_pair_mode.load();
-}
 
 extern "C" int gr_score_splits(int64_t n_users, int64_t n_items) {
   if (n_users <= 0 || n_items <= 0) return 1;
@@ -574,15 +601,18 @@ extern "C" size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items
 }
 
 extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const uint16_t* items_q, int64_t n_items,
-                                int64_t item_id_base, int32_t d_pad, int32_t parts, int32_t elem_type,
-                                const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null,
-                                int32_t shortlist, float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes,
-                                gr_stream_t stream) {
+                                int64_t item_id_base, int32_t d_pad, int32_t parts_users, int32_t parts_items,
+                                int32_t elem_type, const int64_t* bought_indptr_or_null,
+                                const int32_t* bought_ids_or_null, int32_t shortlist, int32_t k,
+                                const float* band_or_null, const int32_t* user_map_or_null, int32_t flags,
+                                float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes, gr_stream_t stream) {
   GR_REQUIRE(n_users >= 0 && n_items >= 0, GR_E_INVALID, "negative size");
   GR_REQUIRE(d_pad == 64 || d_pad == 128, GR_E_INVALID, "d_pad must be 64 or 128 (pad the embeddings with gr_score_prep)");
-  GR_REQUIRE(parts == 1 || parts == 2, GR_E_INVALID, "parts must be 1 (single product) or 2 (hi/lo split, 3 products)");
+  GR_REQUIRE((parts_users == 1 || parts_users == 2) && (parts_items == 1 || parts_items == 2) && parts_items <= parts_users,
+             GR_E_INVALID, "(parts_users, parts_items) must be (1,1), (2,1) or (2,2)");
   GR_REQUIRE(elem_type == GR_ELEM_BF16 || elem_type == GR_ELEM_FP16, GR_E_INVALID, "unknown element type");
   GR_REQUIRE(shortlist >= 1 && shortlist <= 32, GR_E_INVALID, "shortlist must be in [1, 32]");
+  GR_REQUIRE(k >= 1 && k <= shortlist, GR_E_INVALID, "k must be in [1, shortlist]");
   GR_REQUIRE(item_id_base >= 0 && item_id_base + n_items <= 0x7fffffffLL, GR_E_INVALID, "item ids must fit int32");
   if (n_users == 0) return GR_OK;
   GR_REQUIRE(sl_score && sl_id, GR_E_INVALID, "null output");
@@ -600,11 +630,11 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   GR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   GR_REQUIRE(major == 10, GR_E_UNSUPPORTED, "tcgen05 scoring kernel needs an sm_100 device");
   ScoreArgs a;
-  int rc = make_map(&a.mu, users_q, n_users, d_pad * parts, elem_type);
+  int rc = make_map(&a.mu, users_q, n_users, d_pad * parts_users, elem_type);
   if (rc != GR_OK) return rc;
-  rc = make_map(&a.mi, items_q, n_items, d_pad * parts, elem_type);
+  rc = make_map(&a.mi, items_q, n_items, d_pad * parts_items, elem_type);
   if (rc != GR_OK) return rc;
-  rc = make_map(&a.mi_half, items_q, n_items, d_pad * parts, elem_type, TILE_N / 2);
+  rc = make_map(&a.mi_half, items_q, n_items, d_pad * parts_items, elem_type, TILE_N / 2);
   if (rc != GR_OK) return rc;
   a.n_users = n_users; a.n_items = n_items; a.item_id_base = item_id_base;
   a.splits = choose_splits(n_users, n_items);
@@ -613,7 +643,7 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   a.ab_format = elem_type == GR_ELEM_FP16 ? 0u : 1u;
   a.bptr = reinterpret_cast<const long long*>(bought_indptr_or_null);
   a.bids = bought_ids_or_null;
-  a.S = shortlist;
+  a.S = shortlist; a.k = k; a.band = band_or_null; a.user_map = user_map_or_null;
   float* part_score = sl_score;
   int* part_id = sl_id;
   if (a.splits > 1) {
@@ -623,16 +653,9 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
     part_id = reinterpret_cast<int*>(static_cast<char*>(ws) + half);
   }
   a.sl_score = part_score; a.sl_id = part_id;
-  static const int debug_mode = getenv("GR_SCORE_DEBUG_MODE") ? atoi(getenv("GR_SCORE_DEBUG_MODE")) : 0;
-  if (g_pair_mode.load() != 0 && debug_mode == 0 && d_pad == 128) {  // CTA-pair (cta_group::2) kernel: the default
-    rc = parts == 1 ? launch_score<2, 1, 0, true>(a, st) : launch_score<2, 2, 0, true>(a, st);
-  } else
-  if (debug_mode != 0 && d_pad == 128 && parts == 2) {  // pipeline experiments (results are NOT valid top-k lists)
-    rc = debug_mode == 1 ? launch_score<2, 2, 1>(a, st) : debug_mode == 2 ? launch_score<2, 2, 2>(a, st) : launch_score<2, 2, 3>(a, st);
-  } else if (debug_mode != 0 && d_pad == 128 && parts == 1) {
-    rc = debug_mode == 1 ? launch_score<2, 1, 1>(a, st) : debug_mode == 2 ? launch_score<2, 1, 2>(a, st) : launch_score<2, 1, 3>(a, st);
-  } else if (d_pad == 64) rc = parts == 1 ? launch_score<1, 1>(a, st) : launch_score<1, 2>(a, st);
-  else rc = parts == 1 ? launch_score<2, 1>(a, st) : launch_score<2, 2>(a, st);
+  if (d_pad == 64) rc = launch_scheme<1, false>(a, parts_users, parts_items, st);
+  else if (flags & GR_SCORE_FLAG_SINGLE_CTA) rc = launch_scheme<2, false>(a, parts_users, parts_items, st);
+  else rc = launch_scheme<2, true>(a, parts_users, parts_items, st);  // CTA pairs (cta_group::2): the default
   if (rc != GR_OK) return rc;
   if (a.splits > 1)
     return gr_topk_merge(part_score, part_id, a.splits, n_users, shortlist, shortlist, sl_score, sl_id, stream);

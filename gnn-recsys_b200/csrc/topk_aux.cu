@@ -87,6 +87,23 @@ __device__ __forceinline__ float from16(uint16_t b, int elem_type) {
   return __bfloat162float(__ushort_as_bfloat16(b));
 }
 
+// One row -> its 16-bit parts. `w` = the normalised (centred) value of this lane's column q (0 beyond d). Returns this
+// lane's squared residuals: r1 += (w - hi)^2, r2 += (w - hi - lo)^2 (== r1 for parts == 1). Shared by the prep kernel
+// and the re-score kernel, so that the user residuals of the proof are those of the rows the GEMM actually read.
+__device__ __forceinline__ void quantise(float w, int parts, int elem_type, uint16_t& hi, uint16_t& lo, float& r1,
+                                         float& r2) {
+  hi = to16(w, elem_type);
+  const float e1 = w - from16(hi, elem_type);  // exact in fp32
+  r1 = fmaf(e1, e1, r1);
+  lo = 0;
+  float e2 = e1;
+  if (parts == 2) {
+    lo = to16(e1, elem_type);
+    e2 = e1 - from16(lo, elem_type);
+  }
+  r2 = fmaf(e2, e2, r2);
+}
+
 __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict__ x, long long n, int d,
                                                          const float* __restrict__ center, int d_pad, int parts,
                                                          int elem_type, uint16_t* __restrict__ out,
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int nq = d_pad / 32;  // 2 or 4
-  float max_norm = 0.f, min_norm = INFINITY;
+  float max_norm = 0.f, min_norm = INFINITY, max_r1 = 0.f, max_r2 = 0.f;
   for (long long r = warp; r < n; r += n_warps) {
     float v[4];
     float ss = 0.f;
@@ -108,7 +125,7 @@ __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict
     const float nrm = sqrtf(gr::warp_sum(ss));
     if (nrm > 0.f) min_norm = fminf(min_norm, nrm);
     const float inv = 1.f / fmaxf(nrm, 1e-12f);
-    float cs = 0.f;
+    float cs = 0.f, r1 = 0.f, r2 = 0.f;
     uint16_t* o = out + r * (long long)(parts * d_pad);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -118,16 +135,21 @@ __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict
         if (center != nullptr && c < d) w -= __ldg(center + c);
         if (c >= d) w = 0.f;
         cs = fmaf(w, w, cs);
-        const uint16_t hi = to16(w, elem_type);
+        uint16_t hi, lo;
+        quantise(w, parts, elem_type, hi, lo, r1, r2);
         o[c] = hi;
-        if (parts == 2) o[d_pad + c] = to16(w - from16(hi, elem_type), elem_type);
+        if (parts == 2) o[d_pad + c] = lo;
       }
     }
     max_norm = fmaxf(max_norm, sqrtf(gr::warp_sum(cs)));
+    max_r1 = fmaxf(max_r1, sqrtf(gr::warp_sum(r1)));
+    max_r2 = fmaxf(max_r2, sqrtf(gr::warp_sum(r2)));
   }
   if (stats != nullptr && lane == 0) {
     atomicMax(reinterpret_cast<int*>(stats), __float_as_int(max_norm));        // non-negative floats order as ints
     if (min_norm < INFINITY) atomicMin(reinterpret_cast<int*>(stats + 1), __float_as_int(min_norm));
+    atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(max_r2));
+    atomicMax(reinterpret_cast<int*>(stats + 3), __float_as_int(max_r1));
   }
 }
 
@@ -159,15 +181,41 @@ __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { ret
 // ------------------------------------------------------------------------------------------------ rescore
 constexpr int RS_WARPS = 8;
 
+struct RescoreErr {
+  int elem_type, parts_users, parts_items;
+  float acc_err;
+  const float* band;  // device scalar or null
+};
+
+// |approximate - exact| of one (user, item) score: user residuals ru (final) / ru1 (first level), item table
+// statistics Y = max |row|, R / R1 = max final / first-level residual (include/gnn_recsys_b200.h, stage 2)
+__device__ __forceinline__ float score_err(float ru, float ru1, float Y, float R, float R1, int elem_type,
+                                           int parts_users, int parts_items, float acc_err) {
+  const float u_round = elem_type == GR_ELEM_FP16 ? 0x1p-11f : 0x1p-8f;
+  float err = ru * Y + (1.f + ru) * R + acc_err * (1.f + ru) * (Y + R);
+  if (parts_users == 2 && parts_items == 2) err += ru1 * R1 * (1.f + u_round) * (1.f + u_round);
+  return err;
+}
+
+// band = 2 x the largest err_u over the user table (its measured residuals, user stats [2] / [3])
+__global__ void score_band_kernel(const float* __restrict__ item_stats, const float* __restrict__ user_stats,
+                                  RescoreErr em, float* __restrict__ band) {
+  const float ru = user_stats[2] * 1.001f, ru1 = user_stats[3] * 1.001f;
+  band[0] = 2.f * score_err(ru, ru1, item_stats[0], item_stats[2], item_stats[3], em.elem_type, em.parts_users,
+                            em.parts_items, em.acc_err) * 1.001f;
+}
+
 __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
     const float* __restrict__ hu, const float* __restrict__ hi, long long item_id_base, int d,
     const float* __restrict__ center, const float* __restrict__ sl_score, const int* __restrict__ sl_id, int S,
-    long long n_users, const float* __restrict__ stats, float err_rel, float err_abs, float tie_tol, int k, float eps,
-    int* __restrict__ out_ids, float* __restrict__ out_scores, int* __restrict__ overflow_users,
-    int* __restrict__ n_overflow) {
+    long long n_users, const float* __restrict__ stats, RescoreErr em, float tie_tol, int k, float eps,
+    const int* __restrict__ user_map, int* __restrict__ out_ids, float* __restrict__ out_scores,
+    int* __restrict__ overflow_users, int* __restrict__ n_overflow) {
   extern __shared__ __align__(16) float s_user[];  // [RS_WARPS][d]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* xu = s_user + w * d;
+  const float Y = stats[0], min_item = stats[1], R = stats[2], R1 = stats[3];
+  const float band = em.band != nullptr ? __ldg(em.band) : INFINITY;
   for (long long u = (long long)blockIdx.x * RS_WARPS + w; u < n_users; u += (long long)gridDim.x * RS_WARPS) {
     float pn = 0.f, pc = 0.f;
     for (int c = lane; c < d; c += 32) {
@@ -177,7 +225,16 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
       if (center != nullptr) pc = fmaf(x, __ldg(center + c), pc);
     }
     const float nu = gr::warp_sum(pn);
-    const float xc = gr::warp_sum(pc) / fmaxf(sqrtf(nu), 1e-12f);
+    const float inv_nrm = 1.f / fmaxf(sqrtf(nu), 1e-12f);  // the same operations as score_prep_kernel (d <= 128 there)
+    const float xc = gr::warp_sum(pc) * inv_nrm;
+    // rounding residuals of this user's operand row, recomputed exactly as stage 0 rounds it
+    float r1 = 0.f, r2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      uint16_t qh, ql;
+      quantise(xu[c] * inv_nrm, em.parts_users, em.elem_type, qh, ql, r1, r2);
+    }
+    const float ru1 = sqrtf(gr::warp_sum(r1)) * 1.001f, ru = sqrtf(gr::warp_sum(r2)) * 1.001f;
+    const float err = score_err(ru, ru1, Y, R, R1, em.elem_type, em.parts_users, em.parts_items, em.acc_err);
     __syncwarp();
     int id = -1;
     float approx = -INFINITY, e = -INFINITY;
@@ -185,11 +242,20 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
       id = sl_id[u * S + lane];
       approx = sl_score[u * S + lane];
     }
+    const bool valid = id >= 0;
+    const int n_valid = __popc(__ballot_sync(FULL, valid));
+    // a candidate whose approximate score lies more than 2 err below the k-th best approximate score cannot reach the
+    // exact top-k (k candidates score at least tau_k - err exactly): it is neither gathered nor ranked
+    const float tau_k = n_valid >= k ? __shfl_sync(FULL, approx, k - 1) : -INFINITY;
+    const bool cand = valid && approx >= tau_k - 2.f * err;
+    if (!cand) id = -1;
     if ((d & 31) == 0) {
       // 8 lanes per candidate, 4 candidates per pass: every load instruction covers 4 x 128 contiguous bytes
       // (the one-lane-per-candidate walk touched 32 different rows per instruction, half a sector each)
       const int grp = lane >> 3, sub = lane & 7;
+      const unsigned cmask = __ballot_sync(FULL, cand);
       for (int pass = 0; pass * 4 < S; ++pass) {
+        if (((cmask >> (pass * 4)) & 0xfu) == 0u) continue;  // warp-uniform: none of these four is a candidate
         const int cid = __shfl_sync(FULL, id, min(pass * 4 + grp, 31));
         float dot = 0.f, ni = 0.f;
         if (cid >= 0 && pass * 4 + grp < S) {
@@ -215,7 +281,6 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
       dot_norm(xu, hi + (id - item_id_base) * (long long)d, d, dot, ni);
       e = cosine(dot, nu, ni, eps);
     }
-    const bool valid = id >= 0;
     int rank = 0;
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
@@ -223,27 +288,28 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
       const int ii = __shfl_sync(FULL, id, i);
       if (ii >= 0 && i != lane && better(ei, ii, e, id)) ++rank;
     }
-    const int n_valid = __popc(__ballot_sync(FULL, valid));
-    if (valid && rank < k) {
+    const int n_cand = __popc(__ballot_sync(FULL, cand));
+    if (cand && rank < k) {
       out_ids[u * k + rank] = id;
       out_scores[u * k + rank] = e;
     }
-    if (lane >= n_valid && lane < k) {
+    if (lane >= n_cand && lane < k) {
       out_ids[u * k + lane] = -1;
       out_scores[u * k + lane] = -INFINITY;
     }
-    // soundness: a full shortlist may have cut off items that score within the quantisation error of its tail
-    if (n_valid == S) {
-      const float tau = __shfl_sync(FULL, approx, S - 1);
-      const unsigned kth_mask = __ballot_sync(FULL, valid && rank == k - 1);
+    // soundness: every item stage 1 dropped has an approximate score <= dropped
+    float dropped = -INFINITY;
+    if (n_valid == S) dropped = __shfl_sync(FULL, approx, S - 1);
+    if (n_valid >= k) dropped = fmaxf(dropped, tau_k - band);  // band == +inf: -inf, the rule was off
+    if (dropped > -INFINITY) {
+      const unsigned kth_mask = __ballot_sync(FULL, cand && rank == k - 1);
       float kth = -INFINITY;
       if (kth_mask) kth = __shfl_sync(FULL, e, __ffs(kth_mask) - 1);
-      const float bound = tau + err_rel * stats[0] + err_abs + xc;
-      const float min_item = stats[1];
+      const float bound = dropped + err + xc;
       const bool clamp_binds = nu > 0.f && nu * min_item * min_item < eps * eps;
       if (lane == 0 && (S < k || kth < bound - tie_tol || clamp_binds)) {
         const int slot = atomicAdd(n_overflow, 1);
-        overflow_users[slot] = (int)u;
+        overflow_users[slot] = user_map != nullptr ? user_map[u] : (int)u;
       }
     }
     __syncwarp();
@@ -252,12 +318,16 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(
 
 // ------------------------------------------------------------------------------------------------ exact top-k
 constexpr int EX_THREADS = 256;
+constexpr int EX_KMAX = 64;  // entries per pass (per-thread sorted lists of that length live in shared memory)
 
+// One pass writes entries [k_off, k_off + k_pass) of every listed user's k_total-long row: the k_pass best items that
+// come strictly AFTER entry k_off - 1 in the output order (score desc, id asc). k <= EX_KMAX is a single pass; larger k
+// (the reference's get_recs takes any k) costs one sweep over the items per EX_KMAX entries.
 __global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
     const float* __restrict__ hu, const int* __restrict__ user_list, const int* __restrict__ n_list, long long n_users,
     const float* __restrict__ hi, long long n_items, long long item_id_base, int d,
-    const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int k, float eps,
-    const float* __restrict__ popularity, float weight_popularity, int* __restrict__ out_ids,
+    const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int k_total, int k_off, int k,
+    float eps, const float* __restrict__ popularity, float weight_popularity, int* __restrict__ out_ids,
     float* __restrict__ out_scores) {
   extern __shared__ __align__(16) float smem[];
   float* xu = smem;                                            // [d_al]
@@ -273,6 +343,20 @@ __global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
   for (long long idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const long long u = user_list != nullptr ? (long long)user_list[idx] : idx;
     __syncthreads();
+    // resume point of a later pass: everything up to (after_s, after_i) is already in the row
+    float after_s = INFINITY;
+    int after_i = -1;
+    if (k_off > 0) {
+      after_s = out_scores[u * k_total + k_off - 1];
+      after_i = out_ids[u * k_total + k_off - 1];
+      if (after_i < 0) {  // the previous pass ran out of items
+        for (int r = tid; r < k; r += EX_THREADS) {
+          out_ids[u * k_total + k_off + r] = -1;
+          out_scores[u * k_total + k_off + r] = -INFINITY;
+        }
+        continue;
+      }
+    }
     float pn = 0.f;
     for (int c = tid; c < d; c += EX_THREADS) {
       const float x = hu[u * d + c];
@@ -319,6 +403,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
       if (popularity != nullptr) s = fmaf(weight_popularity, __ldg(popularity + i), expf(s - 1.f) * inv_z);
       if (s > tau) {
         const int gid = (int)(item_id_base + i);
+        if (k_off > 0 && !better(after_s, after_i, s, gid)) continue;  // already emitted by an earlier pass
         long long lo = b0, hi_ = b1;
         while (lo < hi_) {
           const long long mid = (lo + hi_) >> 1;
@@ -358,8 +443,8 @@ __global__ void __launch_bounds__(EX_THREADS) exact_topk_kernel(
         if (better(red_s[i], red_i[i], bs, bi)) { bs = red_s[i]; bi = red_i[i]; bt = red_t[i]; }
       const bool none = bi == 0x7fffffff;
       if (tid == 0) {
-        out_ids[u * k + r] = none ? -1 : bi;
-        out_scores[u * k + r] = none ? -INFINITY : bs;
+        out_ids[u * k_total + k_off + r] = none ? -1 : bi;
+        out_scores[u * k_total + k_off + r] = none ? -INFINITY : bs;
       }
       if (!none && tid == bt) ++head;
       __syncthreads();
@@ -421,21 +506,27 @@ __global__ void __launch_bounds__(256) metrics_kernel(const int* __restrict__ re
   unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   for (long long u = warp; u < n_users; u += n_warps) {
     const long long b0 = t_indptr[u], b1 = t_indptr[u + 1];
-    const int id = lane < k ? recs[u * k + lane] : -1;
-    if (id >= 0) {
-      ++c0;
-      long long lo = b0, hi = b1;
-      while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (t_ids[mid] < id) lo = mid + 1; else hi = mid;
+    for (int r0 = 0; r0 < k; r0 += 32) {  // precision side: 32 recommendations per pass
+      const int id = r0 + lane < k ? recs[u * k + r0 + lane] : -1;
+      if (id >= 0) {
+        ++c0;
+        long long lo = b0, hi = b1;
+        while (lo < hi) {
+          const long long mid = (lo + hi) >> 1;
+          if (t_ids[mid] < id) lo = mid + 1; else hi = mid;
+        }
+        if (lo < b1 && t_ids[lo] == id) ++c1;
+        atomicOr(bitmap + (id >> 5), 1u << (id & 31));
       }
-      if (lo < b1 && t_ids[lo] == id) ++c1;
-      atomicOr(bitmap + (id >> 5), 1u << (id & 31));
     }
-    for (long long j = b0 + lane; j < ((b1 - b0 + 31) / 32) * 32 + b0; j += 32) {
+    for (long long j = b0 + lane; j < ((b1 - b0 + 31) / 32) * 32 + b0; j += 32) {  // recall side
       const int t = j < b1 ? t_ids[j] : -2;
       bool hit = false;
-      for (int i = 0; i < k; ++i) hit |= (__shfl_sync(FULL, id, i) == t);
+      for (int r0 = 0; r0 < k; r0 += 32) {
+        const int id = r0 + lane < k ? recs[u * k + r0 + lane] : -1;
+        const int n = min(32, k - r0);
+        for (int i = 0; i < n; ++i) hit |= (__shfl_sync(FULL, id, i) == t);
+      }
       if (j < b1) { ++c2; if (hit) ++c3; }
     }
   }
@@ -468,7 +559,7 @@ extern "C" size_t gr_metrics_workspace_bytes(int64_t n_items) {
 extern "C" int gr_metrics_at_k(const int32_t* recs, int64_t n_users, int32_t k, const int64_t* truth_indptr,
                                const int32_t* truth_ids, int64_t n_items, uint64_t* counters5, void* ws,
                                size_t ws_bytes, gr_stream_t stream) {
-  GR_REQUIRE(n_users >= 0 && k >= 1 && k <= 32 && n_items >= 0, GR_E_INVALID, "bad shape (k must be in [1, 32])");
+  GR_REQUIRE(n_users >= 0 && k >= 1 && n_items >= 0, GR_E_INVALID, "bad shape");
   GR_REQUIRE(counters5 != nullptr, GR_E_INVALID, "null counters");
   GR_REQUIRE(ws != nullptr && ws_bytes >= gr_metrics_workspace_bytes(n_items), GR_E_WORKSPACE, "workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -508,7 +599,7 @@ extern "C" int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, f
 }
 
 extern "C" int gr_score_prep(const float* x, int64_t n, int32_t d, const float* center_or_null, int32_t d_pad,
-                             int32_t parts, int32_t elem_type, uint16_t* out_q, float* stats_or_null,
+                             int32_t parts, int32_t elem_type, uint16_t* out_q, float* stats4_or_null,
                              gr_stream_t stream) {
   GR_REQUIRE(n >= 0 && d > 0, GR_E_INVALID, "bad shape");
   GR_REQUIRE(d_pad == 64 || d_pad == 128, GR_E_INVALID, "d_pad must be 64 or 128");
@@ -519,30 +610,44 @@ extern "C" int gr_score_prep(const float* x, int64_t n, int32_t d, const float* 
   GR_REQUIRE(x && out_q, GR_E_INVALID, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)gr::sm_count() * 16);
-  score_prep_kernel<<<grid, 256, 0, st>>>(x, n, d, center_or_null, d_pad, parts, elem_type, out_q, stats_or_null);
+  score_prep_kernel<<<grid, 256, 0, st>>>(x, n, d, center_or_null, d_pad, parts, elem_type, out_q, stats4_or_null);
   GR_LAUNCH_CHECK();
   return GR_OK;
 }
 
 extern "C" int gr_rescore_topk_f32(const float* h_user, const float* h_item, int64_t item_id_base, int32_t d,
                                    const float* center_or_null, const float* sl_score, const int32_t* sl_id,
-                                   int32_t shortlist, int64_t n_users, const float* stats, float err_rel,
-                                   float err_abs, float tie_tol, int32_t k, float eps, int32_t* out_ids,
-                                   float* out_scores, int32_t* overflow_users, int32_t* n_overflow,
+                                   int32_t shortlist, int64_t n_users, const float* item_stats4, int32_t elem_type,
+                                   int32_t parts_users, int32_t parts_items, float acc_err, const float* band_or_null,
+                                   float tie_tol, int32_t k, float eps, const int32_t* user_map_or_null,
+                                   int32_t* out_ids, float* out_scores, int32_t* overflow_users, int32_t* n_overflow,
                                    gr_stream_t stream) {
   GR_REQUIRE(n_users >= 0 && d > 0 && d <= 4096, GR_E_INVALID, "bad shape");
   GR_REQUIRE(shortlist >= 1 && shortlist <= 32, GR_E_INVALID, "shortlist must be in [1, 32]");
   GR_REQUIRE(k >= 1 && k <= 32, GR_E_INVALID, "k must be in [1, 32]");
+  GR_REQUIRE(elem_type == GR_ELEM_BF16 || elem_type == GR_ELEM_FP16, GR_E_INVALID, "unknown element type");
+  GR_REQUIRE((parts_users == 1 || parts_users == 2) && (parts_items == 1 || parts_items == 2), GR_E_INVALID, "parts must be 1 or 2");
   if (n_users == 0) return GR_OK;
-  GR_REQUIRE(h_user && h_item && sl_score && sl_id && stats && out_ids && out_scores && overflow_users && n_overflow,
+  GR_REQUIRE(h_user && h_item && sl_score && sl_id && item_stats4 && out_ids && out_scores && overflow_users && n_overflow,
              GR_E_INVALID, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (int)std::min<int64_t>((n_users + RS_WARPS - 1) / RS_WARPS, (int64_t)gr::sm_count() * 8);
   const size_t smem = sizeof(float) * RS_WARPS * d;
   if (smem > 48 * 1024) GR_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RescoreErr em{elem_type, parts_users, parts_items, acc_err, band_or_null};
   rescore_kernel<<<grid, RS_WARPS * 32, smem, st>>>(h_user, h_item, item_id_base, d, center_or_null, sl_score, sl_id,
-                                                    shortlist, n_users, stats, err_rel, err_abs, tie_tol, k, eps,
-                                                    out_ids, out_scores, overflow_users, n_overflow);
+                                                    shortlist, n_users, item_stats4, em, tie_tol, k, eps,
+                                                    user_map_or_null, out_ids, out_scores, overflow_users, n_overflow);
+  GR_LAUNCH_CHECK();
+  return GR_OK;
+}
+
+extern "C" int gr_score_band(const float* item_stats4, const float* user_stats4, int32_t elem_type, int32_t parts_users,
+                             int32_t parts_items, float acc_err, float* band, gr_stream_t stream) {
+  GR_REQUIRE(item_stats4 && user_stats4 && band, GR_E_INVALID, "null pointer");
+  GR_REQUIRE(elem_type == GR_ELEM_BF16 || elem_type == GR_ELEM_FP16, GR_E_INVALID, "unknown element type");
+  RescoreErr em{elem_type, parts_users, parts_items, acc_err, nullptr};
+  score_band_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(item_stats4, user_stats4, em, band);
   GR_LAUNCH_CHECK();
   return GR_OK;
 }
@@ -554,21 +659,25 @@ extern "C" int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_
                                        int32_t k, float eps, const float* popularity_or_null, float weight_popularity,
                                        int32_t* out_ids, float* out_scores, gr_stream_t stream) {
   GR_REQUIRE(n_users >= 0 && n_items >= 0 && d > 0 && d <= 4096, GR_E_INVALID, "bad shape");
-  GR_REQUIRE(k >= 1 && k <= 32, GR_E_INVALID, "k must be in [1, 32]");
+  GR_REQUIRE(k >= 1, GR_E_INVALID, "k must be positive");
   GR_REQUIRE(item_id_base >= 0 && item_id_base + n_items <= 0x7fffffffLL, GR_E_INVALID, "item ids must fit int32");
   if (n_users == 0) return GR_OK;
   GR_REQUIRE(h_user && out_ids && out_scores && (n_items == 0 || h_item), GR_E_INVALID, "null pointer");
   GR_REQUIRE(bought_indptr_or_null == nullptr || bought_ids_or_null != nullptr, GR_E_INVALID,
              "bought_indptr without bought_ids");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = sizeof(float) * ((d + 3) & ~3) + (size_t)k * EX_THREADS * 8;
+  const int k_first = std::min<int>(k, EX_KMAX);
+  const size_t smem = sizeof(float) * ((d + 3) & ~3) + (size_t)k_first * EX_THREADS * 8;
   GR_CUDA(cudaFuncSetAttribute(exact_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(n_users, (int64_t)gr::sm_count() * 8);
-  exact_topk_kernel<<<grid, EX_THREADS, smem, st>>>(
-      h_user, user_list_or_null, n_list_or_null, n_users, h_item, n_items, item_id_base, d,
-      reinterpret_cast<const long long*>(bought_indptr_or_null), bought_ids_or_null, k, eps, popularity_or_null,
-      weight_popularity, out_ids, out_scores);
-  GR_LAUNCH_CHECK();
+  for (int k_off = 0; k_off < k; k_off += EX_KMAX) {  // one sweep over the items per EX_KMAX output entries
+    const int k_pass = std::min<int>(EX_KMAX, k - k_off);
+    exact_topk_kernel<<<grid, EX_THREADS, smem, st>>>(
+        h_user, user_list_or_null, n_list_or_null, n_users, h_item, n_items, item_id_base, d,
+        reinterpret_cast<const long long*>(bought_indptr_or_null), bought_ids_or_null, k, k_off, k_pass, eps,
+        popularity_or_null, weight_popularity, out_ids, out_scores);
+    GR_LAUNCH_CHECK();
+  }
   return GR_OK;
 }
 

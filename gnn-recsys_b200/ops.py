@@ -97,44 +97,60 @@ def colmean_normalized(x: torch.Tensor) -> torch.Tensor:
 
 def score_prep(x: torch.Tensor, center: Optional[torch.Tensor], d_pad: int, parts: int, elem_type: int,
                want_stats: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """Quantised operand rows ``[n, parts * d_pad]`` (int16 storage) and ``stats = [max |row - center|, min |row|]``."""
+    """Quantised operand rows ``[n, parts * d_pad]`` (int16 storage) and ``stats = [max |row - center|, min |row|,
+    max final rounding residual, max first-level residual]`` (see include/gnn_recsys_b200.h)."""
     n, d = x.shape
     q = torch.empty((n, parts * d_pad), dtype=torch.int16, device=x.device)
     stats = None
-    if want_stats:
-        stats = torch.tensor([0.0, float('inf')], dtype=torch.float32, device=x.device)
+    if want_stats:  # {0, +inf, 0, 0} built on the device (no pageable H2D copy: capture-safe)
+        stats = torch.zeros(4, dtype=torch.float32, device=x.device)
+        stats[1] = float('inf')
     N.call('gr_score_prep', N.ptr(x), n, d, N.ptr(center) if center is not None else None, d_pad, parts, elem_type,
            N.ptr(q), N.ptr(stats) if stats is not None else None, N.stream())
     return q, stats
 
 
-def score_topk_tc(users_q, items_q, item_id_base: int, d_pad: int, parts: int, elem_type: int, bought_indptr,
-                  bought_ids, shortlist: int):
+def score_topk_tc(users_q, items_q, item_id_base: int, d_pad: int, parts_users: int, parts_items: int, elem_type: int,
+                  bought_indptr, bought_ids, shortlist: int, k: Optional[int] = None, band: Optional[torch.Tensor] = None,
+                  user_map: Optional[torch.Tensor] = None, flags: int = 0):
     n_users, n_items = users_q.shape[0], items_q.shape[0]
     dev = users_q.device
     sl_score = torch.empty((n_users, shortlist), dtype=torch.float32, device=dev)
     sl_id = torch.empty((n_users, shortlist), dtype=torch.int32, device=dev)
     lib = N.load()
     ws = _ws(lib.gr_score_topk_workspace_bytes(n_users, n_items, shortlist), dev, 'score')
-    N.call('gr_score_topk_tc', N.ptr(users_q), n_users, N.ptr(items_q), n_items, item_id_base, d_pad, parts, elem_type,
-           N.ptr(bought_indptr) if bought_indptr is not None else None,
-           N.ptr(bought_ids) if bought_ids is not None else None, shortlist, N.ptr(sl_score), N.ptr(sl_id), N.ptr(ws),
-           ws.numel(), N.stream())
+    N.call('gr_score_topk_tc', N.ptr(users_q), n_users, N.ptr(items_q), n_items, item_id_base, d_pad, parts_users,
+           parts_items, elem_type, N.ptr(bought_indptr) if bought_indptr is not None else None,
+           N.ptr(bought_ids) if bought_ids is not None else None, shortlist, shortlist if k is None else k,
+           N.ptr(band) if band is not None else None, N.ptr(user_map) if user_map is not None else None, flags,
+           N.ptr(sl_score), N.ptr(sl_id), N.ptr(ws), ws.numel(), N.stream())
     return sl_score, sl_id
 
 
-def rescore_topk(h_user, h_item, item_id_base: int, center, sl_score, sl_id, stats, err_rel: float, err_abs: float,
-                 tie_tol: float, k: int, eps: float):
+def score_band(item_stats, user_stats, elem_type: int, parts_users: int, parts_items: int, acc_err: float) -> torch.Tensor:
+    """Device scalar: 2 x the largest scoring error over the user table (the k-th-best margin of the epilogue)."""
+    band = torch.empty(1, dtype=torch.float32, device=item_stats.device)
+    N.call('gr_score_band', N.ptr(item_stats), N.ptr(user_stats), elem_type, parts_users, parts_items, float(acc_err),
+           N.ptr(band), N.stream())
+    return band
+
+
+def rescore_topk(h_user, h_item, item_id_base: int, center, sl_score, sl_id, stats, elem_type: int, parts_users: int,
+                 parts_items: int, acc_err: float, band: Optional[torch.Tensor], tie_tol: float, k: int, eps: float,
+                 user_map: Optional[torch.Tensor] = None, overflow=None, n_overflow=None):
+    """Exact re-score + proof. ``overflow`` / ``n_overflow`` may be passed in to APPEND to an existing list."""
     n_users, d = h_user.shape
     dev = h_user.device
     out_ids = torch.empty((n_users, k), dtype=torch.int32, device=dev)
     out_scores = torch.empty((n_users, k), dtype=torch.float32, device=dev)
-    overflow = torch.empty(max(n_users, 1), dtype=torch.int32, device=dev)
-    n_overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    if overflow is None:
+        overflow = torch.empty(max(n_users, 1), dtype=torch.int32, device=dev)
+        n_overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     N.call('gr_rescore_topk_f32', N.ptr(h_user), N.ptr(h_item), item_id_base, d,
            N.ptr(center) if center is not None else None, N.ptr(sl_score), N.ptr(sl_id), sl_id.shape[1], n_users,
-           N.ptr(stats), err_rel, err_abs, tie_tol, k, eps, N.ptr(out_ids), N.ptr(out_scores), N.ptr(overflow),
-           N.ptr(n_overflow), N.stream())
+           N.ptr(stats), elem_type, parts_users, parts_items, float(acc_err), N.ptr(band) if band is not None else None,
+           float(tie_tol), k, float(eps), N.ptr(user_map) if user_map is not None else None, N.ptr(out_ids),
+           N.ptr(out_scores), N.ptr(overflow), N.ptr(n_overflow), N.stream())
     return out_ids, out_scores, overflow, n_overflow
 
 

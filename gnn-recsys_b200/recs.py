@@ -2,18 +2,22 @@
 
 Pipeline (every stage is a C-ABI call, see include/gnn_recsys_b200.h):
 
-  colmean -> prep(items), prep(users) -> tcgen05 GEMM + fused shortlist -> exact fp32 re-score + soundness proof
-          -> exact fallback for the (rare) users whose shortlist could not be proven complete
+  colmean -> prep(items), prep(users) -> pass 1: tcgen05 GEMM + fused shortlist (ONE fp16 product, shortlist 32)
+          -> exact fp32 re-score + soundness proof per user
+          -> pass 2 for the users pass 1 could not prove: the 3-product hi/lo GEMM (fp32-grade) + re-score + proof
+          -> brute-force fp32 kernel for whoever is left (exact ties filling a whole shortlist)
 
 The GEMM runs on 16-bit operands; the answer does not: the final ids and their order always come from fp32
-cosines (the torch formula the reference calls), and a user only keeps the shortlist answer when the quantisation
-error bound proves that no item outside the shortlist can enter its top-k by more than ``tie_tol`` -- the
-tolerance below which the parity contract (and ``np.argsort`` in the reference) treats scores as tied.
+cosines (the torch formula the reference calls), and a user only keeps a shortlist answer when the MEASURED rounding
+residuals of the operand rows prove that no item outside the shortlist can enter its top-k by more than ``tie_tol``
+-- the tolerance below which the parity contract (and ``np.argsort`` in the reference) treats scores as tied.
+On the BASELINE graphs pass 1 proves > 99 % of the users (tests/experiments/exp_two_product.py), so the tensor pipe
+executes ~1.02 products per useful one instead of 3.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Optional
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
@@ -26,28 +30,60 @@ COS_EPS = 1e-6  # nn.CosineSimilarity(dim=1, eps=1e-6), src/metrics.py:58
 
 @dataclass
 class RecsConfig:
-    elem: str = 'bf16'        # 16-bit operand type of the tensor-core GEMM: 'bf16' | 'fp16'
-    parts: int = 2            # 1 = single product; 2 = hi/lo split, 3 products (hi.hi + lo.hi + hi.lo)
-    shortlist: int = 16       # candidates kept per user by the GEMM epilogue (>= k, <= 32)
-    center: bool = True       # subtract the mean normalised item row (ranking-invariant, shrinks the error bound)
-    tie_tol: float = 1e-5     # score gap treated as a tie (north_star parity rule); 0 = strict
-    acc_err: float = 1.5e-6   # allowance for fp32 accumulation error of the tensor-core sum, relative to |x||y|
-    exact_only: bool = False  # skip the tensor-core path (brute-force fp32 kernel for every user)
+    elem: str = 'fp16'            # 16-bit operand type of the tensor-core GEMM: 'fp16' | 'bf16'
+    parts_users: int = 1          # parts per user row: 1 = hi, 2 = hi + lo
+    parts_items: int = 1          # parts per item row; (1,1) 1 product, (2,1) 2 products, (2,2) 3 products
+    shortlist: int = 32           # candidates kept per user by the GEMM epilogue (>= k, <= 32)
+    second: Optional[Tuple[str, int, int, int]] = ('fp16', 2, 2, 16)  # (elem, parts_users, parts_items, shortlist) of
+    #                               pass 2 over the users pass 1 cannot prove; None = straight to the exact kernel
+    center: bool = True           # subtract the mean normalised item row (ranking-invariant, shrinks the error bound)
+    k_band: bool = True           # epilogue threshold max(S-th best, k-th best - 2 err) instead of the S-th best alone
+    tie_tol: float = 1e-5         # score gap treated as a tie (north_star parity rule); 0 = strict
+    acc_err: float = 1.5e-6       # allowance for fp32 accumulation error of the tensor-core sum, relative to |x||y|
+    exact_only: bool = False      # skip the tensor-core path (brute-force fp32 kernel for every user)
+    single_cta: bool = False      # cta_group::1 kernel instead of CTA pairs (same results; tests / experiments)
+    parts: Optional[int] = None   # shorthand: parts=1 -> (1, 1), parts=2 -> (2, 2) and no second pass
+
+    def __post_init__(self):
+        if self.parts is not None:
+            self.parts_users = self.parts_items = int(self.parts)
+            if self.parts == 2:
+                self.second = None
+        if (self.parts_users, self.parts_items) not in ((1, 1), (2, 1), (2, 2)):
+            raise ValueError('(parts_users, parts_items) must be (1, 1), (2, 1) or (2, 2)')
+        if self.second is not None and (self.second[1], self.second[2]) == (self.parts_users, self.parts_items) \
+                and self.second[0] == self.elem:
+            self.second = None
 
     @property
     def elem_type(self) -> int:
-        return {'bf16': N.ELEM_BF16, 'fp16': N.ELEM_FP16}[self.elem]
+        return elem_type_of(self.elem)
 
-    def err_rel(self) -> float:
-        """Worst-case |approx - exact| / (|x| |y|) of the quantised product scheme (unit roundoff u per operand:
-        single product 2u + u^2; split scheme 3u^2 (1 + u)^2), plus the accumulation allowance."""
-        u = 2.0 ** -9 if self.elem == 'bf16' else 2.0 ** -11
-        q = (2 * u + u * u) if self.parts == 1 else 3 * u * u * (1 + u) ** 2
-        return q + self.acc_err
+    @property
+    def products(self) -> int:
+        return {(1, 1): 1, (2, 1): 2, (2, 2): 3}[(self.parts_users, self.parts_items)]
 
-    def err_abs(self, d: int) -> float:
-        """fp16 only: lo halves and tiny values are subnormal (absolute spacing 2^-24): (|x|_1 + |y|_1) 2^-25."""
-        return 0.0 if self.elem == 'bf16' else 2.0 * (d ** 0.5) * 2.0 ** -25
+    @property
+    def flags(self) -> int:
+        return N.SCORE_FLAG_SINGLE_CTA if self.single_cta else 0
+
+
+def elem_type_of(elem: str) -> int:
+    return {'bf16': N.ELEM_BF16, 'fp16': N.ELEM_FP16}[elem]
+
+
+def score_err_bound(ru: float, ru1: float, item_stats, elem: str, parts_users: int, parts_items: int,
+                    acc_err: float) -> float:
+    """Host mirror of the device formula (``score_err`` in csrc/topk_aux.cu): |approximate - exact| of any score of a
+    user whose operand row has rounding residuals ``ru`` (final) / ``ru1`` (first level) against an item table with
+    statistics ``item_stats = [Y, min |x|, R, R1]``:
+    ``s - a = (x - xq).y + xq.(y - yq) [+ x_lo.y_lo for the 3-product scheme] + accumulation``."""
+    Y, _, R, R1 = [float(v) for v in item_stats]
+    u = 2.0 ** -11 if elem == 'fp16' else 2.0 ** -8
+    err = ru * Y + (1 + ru) * R + acc_err * (1 + ru) * (Y + R)
+    if parts_users == 2 and parts_items == 2:
+        err += ru1 * R1 * (1 + u) ** 2
+    return err
 
 
 class BoughtCSR:
@@ -119,7 +155,8 @@ class BoughtCSR:
 
 
 class ScoringTable:
-    """Item side of the scoring GEMM, prepared once per embedding table: quantised rows, centre, error stats."""
+    """Item side of the scoring GEMM, prepared once per embedding table: quantised rows, centre, residual stats.
+    ``operands(elem, parts)`` prepares (and caches) the item operand of another scheme on demand (pass 2)."""
 
     def __init__(self, h_item: torch.Tensor, cfg: RecsConfig, item_id_base: int = 0):
         self.h_item = h_item.contiguous()
@@ -127,11 +164,37 @@ class ScoringTable:
         self.n_items, self.d = h_item.shape
         self.tc = (not cfg.exact_only) and self.d <= 128 and self.n_items > 0
         self.center, self.items_q, self.stats = None, None, None
+        self._ops = {}
         if self.tc:
             self.d_pad = 64 if self.d <= 64 else 128
             if cfg.center:
                 self.center = ops.colmean_normalized(self.h_item)
-            self.items_q, self.stats = ops.score_prep(self.h_item, self.center, self.d_pad, cfg.parts, cfg.elem_type, True)
+            self.items_q, self.stats = self.operands(cfg.elem, cfg.parts_items)
+
+    def operands(self, elem: str, parts: int):
+        key = (elem, parts)
+        if key not in self._ops:
+            self._ops[key] = ops.score_prep(self.h_item, self.center, self.d_pad, parts, elem_type_of(elem), True)
+        return self._ops[key]
+
+
+def _tc_pass(h_user, table: ScoringTable, k: int, bptr, bids, scheme, cfg: RecsConfig, user_map=None, mark=None):
+    """One tensor-core pass: prep(users) -> GEMM + shortlist -> exact re-score + proof.
+    Returns ``(ids, scores, overflow list, n_overflow)``; overflow entries are ``user_map`` values when given."""
+    elem, pu, pi, shortlist = scheme
+    et = elem_type_of(elem)
+    shortlist = max(shortlist, k)
+    items_q, item_stats = table.operands(elem, pi)
+    users_q, user_stats = ops.score_prep(h_user, None, table.d_pad, pu, et, cfg.k_band)
+    band = ops.score_band(item_stats, user_stats, et, pu, pi, cfg.acc_err) if cfg.k_band else None
+    if mark:
+        mark('score_begin')
+    sl_score, sl_id = ops.score_topk_tc(users_q, items_q, table.item_id_base, table.d_pad, pu, pi, et, bptr, bids,
+                                        shortlist, k, band, user_map, cfg.flags)
+    if mark:
+        mark('score_end')
+    return ops.rescore_topk(h_user, table.h_item, table.item_id_base, table.center, sl_score, sl_id, item_stats, et, pu,
+                            pi, cfg.acc_err, band, cfg.tie_tol, k, COS_EPS, user_map)
 
 
 def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Optional[BoughtCSR] = None,
@@ -140,7 +203,8 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
     """Top-``k`` items of ``table`` for every row of ``h_user`` (``[n, d]`` fp32, CUDA): ``(ids int32 [n, k],
     scores fp32 [n, k])`` sorted by (score desc, id asc); ``-1`` / ``-inf`` pad rows with fewer than k candidates.
     ``bought`` rows must follow ``h_user`` rows. ids are global (``table.item_id_base`` added).
-    ``mark(name)`` (optional) is called between stages -- bench.py records CUDA events with it."""
+    ``mark(name)`` (optional) is called between stages -- bench.py records CUDA events with it.
+    ``return_overflow``: also return ``(users sent to pass 2, users sent to the exact kernel)`` as Python ints."""
     mark = mark or (lambda name: None)
     cfg = table.cfg
     h_user = h_user.contiguous()
@@ -149,23 +213,32 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
     bptr, bids = (None, None) if bought is None else bought.on(dev)
     if bought is not None and bought.n_rows != n:
         raise ValueError('bought rows (%d) do not match user rows (%d)' % (bought.n_rows, n))
-    if popularity is not None or not table.tc:
-        # popularity re-rank (softmax over ALL items + w * popularity) runs on the exact fp32 kernel only
+    if popularity is not None or not table.tc or k > 32:
+        # popularity re-rank (softmax over ALL items + w * popularity), embeddings wider than 128 and k > 32 (the fused
+        # epilogue keeps at most 32 candidates) run on the exact fp32 kernel: any k, one item sweep per 64 entries
         ids, scores = ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS,
                                            popularity=popularity, weight_popularity=weight_popularity)
-        return (ids, scores, torch.zeros(1, dtype=torch.int32, device=dev)) if return_overflow else (ids, scores)
-    shortlist = max(cfg.shortlist, k)
-    if shortlist > 32:
-        raise ValueError('k / shortlist above 32 is not supported by the fused top-k epilogue')
-    users_q, _ = ops.score_prep(h_user, None, table.d_pad, cfg.parts, cfg.elem_type, False)
-    mark('score_begin')
-    sl_score, sl_id = ops.score_topk_tc(users_q, table.items_q, table.item_id_base, table.d_pad, cfg.parts,
-                                        cfg.elem_type, bptr, bids, shortlist)
-    mark('score_end')
-    ids, scores, overflow, n_overflow = ops.rescore_topk(
-        h_user, table.h_item, table.item_id_base, table.center, sl_score, sl_id, table.stats, cfg.err_rel(),
-        cfg.err_abs(table.d), cfg.tie_tol, k, COS_EPS)
-    # users whose shortlist could not be proven complete: exact fp32 pass (device-side count, no host sync)
-    ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS, user_list=overflow,
-                         n_list=n_overflow, out_ids=ids, out_scores=scores)
-    return (ids, scores, n_overflow) if return_overflow else (ids, scores)
+        return (ids, scores, (0, 0)) if return_overflow else (ids, scores)
+    if cfg.shortlist > 32:
+        raise ValueError('shortlist above 32 is not supported by the fused top-k epilogue')
+    first = (cfg.elem, cfg.parts_users, cfg.parts_items, cfg.shortlist)
+    ids, scores, overflow, n_overflow = _tc_pass(h_user, table, k, bptr, bids, first, cfg, mark=mark)
+    mark('rescore_end')
+    n1 = n2 = 0
+    if n > 0:
+        n1 = int(n_overflow.item())  # the one host read of the pipeline: sizes pass 2 (usually < 1 % of the users)
+    if n1 > 0 and cfg.second is not None:
+        # pass 2: the users pass 1 could not prove, compacted, through the more accurate scheme
+        rows = overflow[:n1].sort().values  # ascending: deterministic whatever order the proof kernel appended in
+        ids2, scores2, overflow, n_overflow = _tc_pass(h_user[rows.long()], table, k, bptr, bids, cfg.second, cfg,
+                                                       user_map=rows)
+        ids[rows.long()] = ids2
+        scores[rows.long()] = scores2
+        n2 = int(n_overflow.item())
+    else:
+        n2 = n1
+    if n2 > 0:  # exact fp32 pass for whoever is left (device-side list)
+        ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS, user_list=overflow,
+                             n_list=n_overflow, out_ids=ids, out_scores=scores)
+    mark('fallback_end')
+    return (ids, scores, (n1, n2)) if return_overflow else (ids, scores)

@@ -93,22 +93,33 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *  stage 0  gr_score_prep: rows are L2-normalised (x / max(|x|, 1e-12)), optionally shifted by `center`
  *           (the ranking per user is invariant to a common item shift; it shrinks the quantisation error bound),
  *           zero-padded to d_pad (64 or 128) and rounded to 16 bit (GR_ELEM_BF16 | GR_ELEM_FP16). parts == 2 stores a
- *           hi and a lo half per row ([hi d_pad | lo d_pad], x = hi + lo up to 2^-18 / 2^-22 relative) for the
- *           3-product scheme hi.hi + lo.hi + hi.lo. stats[0] (caller-initialised 0) receives max_i |row_i - center|
- *           (atomic max) and stats[1] (caller-initialised +inf) the smallest non-zero |x_i| (atomic min); the
- *           first bounds the scoring error, the second tells stage 2 when the eps clamp of the cosine can bind.
+ *           hi and a lo half per row ([hi d_pad | lo d_pad], x = hi + lo up to 2^-18 / 2^-22 relative).
+ *           stats (float[4], caller-initialised {0, +inf, 0, 0}; atomic max / min over the rows):
+ *             [0] max_i |row_i - center|            [1] smallest non-zero |x_i| (tells stage 2 when the eps clamp of
+ *             [2] max_i |w_i - (hi_i + lo_i)|           the cosine can bind)
+ *             [3] max_i |w_i - hi_i|                 (w = the normalised, centred row; [2] == [3] for parts == 1)
+ *           i.e. the MEASURED rounding residuals of the table, which bound the scoring error of stage 1.
  *           gr_colmean_normalized_f32 computes a deterministic `center` (mean of the normalised rows).
  *  stage 1  gr_score_topk_tc: TMA-fed tcgen05 GEMM users x items^T (16-bit in, fp32 accumulate in TMEM) with a
- *           fused per-user running top-`shortlist` epilogue that skips already-bought items. Bought lists are a CSR
- *           per user (int64 indptr, int32 ids sorted ascending, GLOBAL item ids, duplicates allowed). Output: per
- *           user the `shortlist` best approximate (centred) scores, descending, and their global item ids (-1 = empty
- *           slot).
+ *           fused per-user running shortlist epilogue that skips already-bought items. (parts_users, parts_items)
+ *           selects the product scheme: (1,1) hi.hi; (2,1) hi.hi + lo.hi; (2,2) hi.hi + lo.hi + hi.lo. Bought lists
+ *           are a CSR per user (int64 indptr, int32 ids sorted ascending, GLOBAL item ids, duplicates allowed).
+ *           A candidate enters the list when its score beats max(S-th best so far, k-th best so far - *band)
+ *           (band: device float, NULL = +inf = plain S-th-best rule). user_map (optional int32[n_users]): row u's
+ *           bought list is that of user user_map[u] (second pass over a compacted user subset). Output: per user `shortlist` approximate
+ *           (centred) scores, descending, and their global item ids (-1 = empty slot).
+ *           flags: GR_SCORE_FLAG_SINGLE_CTA = cta_group::1 kernel instead of CTA pairs (same results).
  *  stage 2  gr_rescore_topk_f32: exact fp32 cosine (torch formula x.y / sqrt(max(|x|^2 |y|^2, eps^2))) of the
- *           shortlisted items, sorted by (score desc, id asc), first k. Proves per user that no item outside the
- *           shortlist can enter the top-k by more than tie_tol: with tau = the shortlist's last approximate score and
- *           err = err_rel * stats[0] + err_abs, every outside item scores <= tau + err (+ x.center) exactly; users for
- *           which kth_exact < that bound - tie_tol are appended to overflow_users / n_overflow (caller zero-initialises
- *           n_overflow) and must be recomputed by stage 3.
+ *           shortlisted items that can still reach the top-k, sorted by (score desc, id asc), first k. Proves per user
+ *           that no item outside the shortlist can enter the top-k by more than tie_tol. With the user's own rounding
+ *           residuals r_u (final) and r1_u (first level), recomputed here exactly as stage 0 rounds,
+ *             err_u = r_u*Y + (1 + r_u)*R + [parts_users == parts_items == 2] r1_u*R1*(1 + u)^2 + acc_err*(1 + r_u)*(Y + R)
+ *           (Y, R, R1 = item stats [0], [2], [3]; u = unit roundoff of elem_type) bounds |approx - exact| of every
+ *           item, and every item stage 1 dropped has approx <= dropped = max(tau_S if the list is full, tau_k - *band).
+ *           Users with kth_exact < dropped + err_u + x.center - tie_tol are appended to overflow_users / n_overflow
+ *           (caller zero-initialises n_overflow) and must be recomputed by a more accurate scheme or by stage 3.
+ *           user_map (optional int32[n_users]): overflow entries are user_map[u] instead of u (second pass over a
+ *           compacted user subset).
  *  stage 3  gr_score_topk_exact_f32: exact fp32 scoring of all items for the listed users (the overflow list, or
  *           every user when user_list == NULL): the always-correct fallback and the brute-force checker. With
  *           popularity != NULL it ranks by softmax_i(cos) + weight * popularity_i instead (use_popularity branch of
@@ -116,26 +127,29 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *  merge    gr_topk_merge: row-wise merge of `parts` partial (score desc, id) lists into the k_out best
  *           (scores[p][u][k_in]); ties by smaller id; ids < 0 are empty slots. */
 enum { GR_ELEM_BF16 = 0, GR_ELEM_FP16 = 1 };
+enum { GR_SCORE_FLAG_SINGLE_CTA = 1 };
 #define GR_SCORE_MAX_SPLITS 32
 size_t gr_colmean_workspace_bytes(int64_t n, int32_t d);
 int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, float* center, void* ws, size_t ws_bytes,
                               gr_stream_t stream);
 int gr_score_prep(const float* x, int64_t n, int32_t d, const float* center_or_null, int32_t d_pad, int32_t parts,
-                  int32_t elem_type, uint16_t* out_q, float* stats_or_null, gr_stream_t stream);
+                  int32_t elem_type, uint16_t* out_q, float* stats4_or_null, gr_stream_t stream);
 int gr_score_splits(int64_t n_users, int64_t n_items);
-/* stage-1 kernel variant: 1 = CTA pairs (tcgen05 cta_group::2, M = 256, each CTA holds half of every item tile;
- * default), 0 = single CTA (cta_group::1). Pass a negative value to query. Same results, ~5 % apart under power cap. */
-int gr_score_pair_mode(int set_or_negative);
 size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t shortlist);
 int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const uint16_t* items_q, int64_t n_items,
-                     int64_t item_id_base, int32_t d_pad, int32_t parts, int32_t elem_type,
+                     int64_t item_id_base, int32_t d_pad, int32_t parts_users, int32_t parts_items, int32_t elem_type,
                      const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t shortlist,
+                     int32_t k, const float* band_or_null, const int32_t* user_map_or_null, int32_t flags,
                      float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes, gr_stream_t stream);
+/* *band = 2 x the largest err_u of stage 2 over a user table whose gr_score_prep statistics are user_stats4 */
+int gr_score_band(const float* item_stats4, const float* user_stats4, int32_t elem_type, int32_t parts_users,
+                  int32_t parts_items, float acc_err, float* band, gr_stream_t stream);
 int gr_rescore_topk_f32(const float* h_user, const float* h_item, int64_t item_id_base, int32_t d,
                         const float* center_or_null, const float* sl_score, const int32_t* sl_id, int32_t shortlist,
-                        int64_t n_users, const float* stats, float err_rel, float err_abs, float tie_tol, int32_t k,
-                        float eps, int32_t* out_ids, float* out_scores, int32_t* overflow_users, int32_t* n_overflow,
-                        gr_stream_t stream);
+                        int64_t n_users, const float* item_stats4, int32_t elem_type, int32_t parts_users,
+                        int32_t parts_items, float acc_err, const float* band_or_null, float tie_tol, int32_t k,
+                        float eps, const int32_t* user_map_or_null, int32_t* out_ids, float* out_scores,
+                        int32_t* overflow_users, int32_t* n_overflow, gr_stream_t stream);
 int gr_score_topk_exact_f32(const float* h_user, const int32_t* user_list_or_null, const int32_t* n_list_or_null,
                             int64_t n_users, const float* h_item, int64_t n_items, int64_t item_id_base, int32_t d,
                             const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t k,

@@ -2,7 +2,10 @@
 
 Run in the build container only (needs /root/reference, which does not exist on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [group ...]      groups: embedding popularity sport forward metrics loss (default: all)
+
+``generate(out_dir, groups)`` is what tests/test_golden_regen.py calls to prove that the committed fixtures are exactly
+what this script writes today (every array compared bit for bit).
 
 The reference's unmodified ``src/model.py`` (ConvModel, max_margin_loss), ``src/train/run.py::get_embeddings``
 and ``src/metrics.py::{get_recs, create_already_bought}`` are imported from /root/reference and executed on CPU
@@ -27,10 +30,11 @@ sys.path[:0] = [os.path.join(ROOT, 'oracle', 'dgl_shim'), REFERENCE, ROOT]
 import dgl  # noqa: E402  (the shim)
 from src.model import ConvModel, max_margin_loss  # noqa: E402  (reference, verbatim)
 from src.train.run import get_embeddings  # noqa: E402
-from src.metrics import get_recs, create_already_bought  # noqa: E402
+from src.metrics import get_recs, create_already_bought, recs_to_metrics, get_metrics_at_k  # noqa: E402
 
 import gnn_recsys_b200 as grb  # noqa: E402  (host-side containers only: synthetic data + block building)
 
+OUT_DIR = HERE  # generate() redirects this
 REL = [('user', 'buys', 'item'), ('item', 'bought-by', 'user'), ('user', 'clicks', 'item'), ('item', 'clicked-by', 'user')]
 
 
@@ -80,7 +84,7 @@ def save_case(name, meta, arrays):
     flat = {'meta': np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
     for k, v in arrays.items():
         flat[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
-    path = os.path.join(HERE, name + '.npz')
+    path = os.path.join(OUT_DIR, name + '.npz')
     np.savez_compressed(path, **flat)
     print('wrote %-34s %7.1f KB' % (name + '.npz', os.path.getsize(path) / 1024))
 
@@ -184,7 +188,7 @@ def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, ba
     save_case(name, meta, arrays)
 
 
-def main():
+def main_embedding():
     T = dict(n_users=50, n_items=20, n_edges=300)
     for agg in ('mean', 'mean_nn', 'pool_nn', 'mean_edge', 'pool_nn_edge'):
         embedding_case('tiny_%s' % agg, seed=3, n_layers=3, hidden=16, out=8, aggregator=agg, **T)
@@ -198,17 +202,13 @@ def main():
     # model-sized dims of configs c1/c2 (2-layer mean 128/128) and c3 (3-layer pool_nn hidden 256)
     embedding_case('small_mean_128', 400, 150, 6000, seed=9, n_layers=2, hidden=128, out=128, aggregator='mean')
     embedding_case('small_pool_256', 200, 80, 3000, seed=10, n_layers=3, hidden=256, out=128, aggregator='pool_nn')
-    forward_case('fwd_fanout_mean', 300, 120, 5000, seed=11, hidden=32, out=16, fanouts=[10, 10], batch=64, neg_k=20)
 
-
-if __name__ == '__main__' and len(sys.argv) == 1:
-    main()
 
 
 def popularity_case(base_name, weight, seed):
     """use_popularity branch of the reference's get_recs (src/metrics.py:69-72) on the embeddings of an existing
     fixture: item popularity = share of purchases (like src/builder.py:472-491 a [I, 1] float tensor)."""
-    z = np.load(os.path.join(HERE, base_name + '.npz'))
+    z = np.load(os.path.join(OUT_DIR, base_name + '.npz'))
     meta = json.loads(bytes(z['meta']).decode())
     n_users, n_items, k = meta['n_users'], meta['n_items'], meta['k']
     rel = {c: (torch.from_numpy(z['edges/%s/src' % c[1]]), torch.from_numpy(z['edges/%s/dst' % c[1]])) for c in REL}
@@ -235,8 +235,6 @@ def main_popularity():
     popularity_case('small_mean_128', 0.5, 1)
 
 
-if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'popularity':
-    main_popularity()
 
 
 SPORT_REL = [('item', 'utilized-for', 'sport'), ('sport', 'utilizes', 'item'), ('user', 'practices', 'sport'),
@@ -293,18 +291,111 @@ def sport_case(name, aggregator, seed, n_layers=3, hidden=16, out=8, n_users=50,
     save_case(name, meta, arrays)
 
 
-if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sport':
+def main_sport():
     sport_case('sport_mean_edge', 'mean_edge', 21)
     sport_case('sport_pool_nn', 'pool_nn', 22)
 
 
-def main_forward_extra():
-    """More training-step forwards (config 4 shape) at dims that take the fused tensor-core ConvLayer kernel on SAMPLED
-    blocks (n_src != n_dst, destination prefix), incl. the full-neighbour sampler and a pool_nn stack with fc_preagg."""
+def main_forward():
+    """Training-step forwards (config 4 shape), incl. dims that take the fused tensor-core ConvLayer kernel on SAMPLED
+    blocks (n_src != n_dst, destination prefix), the full-neighbour sampler and a pool_nn stack with fc_preagg."""
+    forward_case('fwd_fanout_mean', 300, 120, 5000, seed=11, hidden=32, out=16, fanouts=[10, 10], batch=64, neg_k=20)
     forward_case('fwd_fanout_mean_128', 400, 150, 6000, seed=12, hidden=128, out=128, fanouts=[10, 10], batch=128, neg_k=50)
     forward_case('fwd_full_pool_nn', 300, 120, 5000, seed=13, hidden=128, out=64, fanouts=[0, 0], batch=64, neg_k=20,
                  aggregator='pool_nn', full=True)
 
 
-if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'forward':
-    main_forward_extra()
+def metrics_case(base_name, seed, k_big):
+    """recs_to_metrics / get_metrics_at_k of the reference (src/metrics.py:81-134) on the embeddings of an existing
+    fixture. Ground truth = random (user, item) pairs with duplicate pairs and users without any recommendation hit;
+    `recs` come from the reference's own get_recs (k from the base case, and k_big > 32 for the large-k path)."""
+    z = np.load(os.path.join(OUT_DIR, base_name + '.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    n_users, n_items, k = meta['n_users'], meta['n_items'], meta['k']
+    rel = {c: (torch.from_numpy(z['edges/%s/src' % c[1]]), torch.from_numpy(z['edges/%s/dst' % c[1]])) for c in REL}
+    g = dgl.heterograph(rel, {'user': n_users, 'item': n_items})
+    y = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    rng = np.random.default_rng(seed)
+    n_gt = 3 * n_users
+    gt_users = rng.integers(0, n_users, n_gt)
+    gt_users[gt_users % 7 == 3] = 0                      # some users absent from the ground truth, user 0 heavy
+    gt_items = rng.integers(0, n_items, n_gt)
+    gt_users[5:9], gt_items[5:9] = gt_users[5], gt_items[5]   # duplicate ground-truth pairs (counted like the reference)
+    uids = np.unique(gt_users)
+    bought_eids = g.out_edges(u=torch.from_numpy(uids), form='eid', etype='buys')
+    out = {'gt_users': gt_users.astype(np.int64), 'gt_items': gt_items.astype(np.int64), 'bought_eids': bought_eids}
+    with torch.no_grad(), redirect_stdout(io.StringIO()):
+        for kk in (k, k_big):
+            for rm in (True, False):
+                p, r, c = get_metrics_at_k(y, g, None, meta['out'], (gt_users, gt_items), bought_eids, kk, rm, False,
+                                           None, 'cos', False, 1)                                   # reference code
+                out['metrics/k%d/remove%d' % (kk, int(rm))] = np.array([p, r, c], dtype=np.float64)
+        # recs_to_metrics alone on hand-made, ragged recommendation lists (incl. an empty one)
+        recs = {int(u): rng.choice(n_items, int(rng.integers(0, 6)), replace=False).tolist() for u in uids.tolist()}
+        recs[int(uids[0])] = []
+        from src.metrics import create_ground_truth
+        p, r, c = recs_to_metrics(recs, create_ground_truth(gt_users, gt_items), g)                 # reference code
+    lens = np.array([len(recs[int(u)]) for u in uids.tolist()], dtype=np.int64)
+    out['ragged/users'], out['ragged/lens'] = uids.astype(np.int64), lens
+    out['ragged/items'] = np.array([i for u in uids.tolist() for i in recs[int(u)]], dtype=np.int64)
+    out['ragged/metrics'] = np.array([p, r, c], dtype=np.float64)
+    save_case(base_name + '_metrics', dict(base=base_name, k=k, k_big=k_big, seed=seed), out)
+
+
+def main_metrics():
+    metrics_case('tiny_mean', 31, 13)          # 20 items: k_big = 13 leaves rows with fewer than k candidates
+    metrics_case('small_mean_128', 32, 40)     # k = 40 > 32
+
+
+def loss_case(base_name, seed):
+    """max_margin_loss of the reference (src/model.py:473-533) with remove_false_negative and / or use_recency on the
+    positive / negative scores of an existing forward fixture. negative_mask = has_edges_between as float
+    (src/train/run.py:100-101), recency only for 'buys' (the KeyError branch covers the etypes without it)."""
+    z = np.load(os.path.join(OUT_DIR, base_name + '.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    neg_k, delta = meta['neg_k'], meta['delta']
+    rng = np.random.default_rng(seed)
+    pos, neg, mask, rec = {}, {}, {}, {}
+    for c in REL:
+        key = 'pos/%s/score' % c[1]
+        if key not in z.files or z[key].shape[0] == 0:
+            continue
+        pos[c], neg[c] = torch.from_numpy(z[key]), torch.from_numpy(z['neg/%s/score' % c[1]])
+        mask[c] = torch.from_numpy((rng.random(neg[c].shape[0]) < 0.15).astype(np.float32))
+    rec[REL[0]] = torch.from_numpy((1.0 + 9.0 * rng.random(pos[REL[0]].shape[0])).astype(np.float32))
+    out = {}
+    for c in pos:
+        out['mask/%s' % c[1]] = mask[c]
+    out['recency/buys'] = rec[REL[0]]
+    for rfn in (False, True):
+        for ur in (False, True):
+            with torch.no_grad():
+                l = max_margin_loss(pos, neg, delta, neg_k, use_recency=ur, recency_scores=rec,
+                                    remove_false_negative=rfn, negative_mask=mask)                   # reference code
+            out['loss/mask%d/recency%d' % (int(rfn), int(ur))] = l
+    save_case(base_name + '_loss', dict(base=base_name, neg_k=neg_k, delta=delta, seed=seed), out)
+
+
+def main_loss():
+    loss_case('fwd_fanout_mean', 41)
+    loss_case('fwd_fanout_mean_128', 42)
+
+
+GROUPS = {'embedding': main_embedding, 'popularity': main_popularity, 'sport': main_sport, 'forward': main_forward,
+          'metrics': main_metrics, 'loss': main_loss}   # in dependency order (popularity / metrics / loss read base cases)
+
+
+def generate(out_dir=HERE, groups=None):
+    global OUT_DIR
+    OUT_DIR = out_dir
+    os.makedirs(out_dir, exist_ok=True)
+    try:
+        for name, fn in GROUPS.items():
+            if groups is None or name in groups:
+                fn()
+    finally:
+        OUT_DIR = HERE
+
+
+if __name__ == '__main__':
+    generate(HERE, sys.argv[1:] or None)

@@ -106,7 +106,7 @@ def test_topk_of_sampled_users_matches_the_brute_force_kernel(world):
     assert bool((srt[:, 1:] != srt[:, :-1]).all())             # no duplicate recommendation
     for r in sample[:300].tolist():                             # nothing already bought
         assert not set(ids[r].tolist()) & set(bought[r])
-    assert int(n_over) < U // 100
+    assert n_over[0] < U // 20 and n_over[1] < U // 1000  # pass 1 proves > 95 %, pass 2 nearly everyone else
 
 
 def test_device_frontier_properties_at_full_size(world):

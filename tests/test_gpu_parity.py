@@ -76,7 +76,9 @@ def test_embeddings_minibatch_loader(grb, name):
         np.testing.assert_allclose(y[t].numpy(), z['emb/' + t], rtol=RTOL, atol=ATOL)
 
 
-RECS_CONFIGS = [dict(elem='bf16', parts=2), dict(elem='fp16', parts=2), dict(elem='bf16', parts=1),
+RECS_CONFIGS = [dict(), dict(parts_users=2, parts_items=1), dict(k_band=False, shortlist=16), dict(single_cta=True),
+                dict(second=None), dict(elem='bf16', second=('bf16', 2, 2, 16)),
+                dict(elem='bf16', parts=2), dict(elem='fp16', parts=2), dict(elem='bf16', parts=1),
                 dict(elem='fp16', parts=1, center=False), dict(exact_only=True), dict(elem='bf16', parts=2, tie_tol=0.0)]
 
 
@@ -157,6 +159,68 @@ def test_metrics_at_k_match_reference_formula(grb):
     wp, wr, wc = O.recs_to_metrics({u: [int(i) for i in v] for u, v in recs.items()}, truth, meta['n_items'])
     assert (p, r, c) == (wp, wr, wc)
     assert grb.recs_to_metrics(recs, truth, g) == (wp, wr, wc)
+
+
+@pytest.mark.parametrize('name', ['tiny_mean', 'small_mean_128'])
+def test_metrics_match_reference_fixture(grb, name):
+    """Device get_metrics_at_k / recs_to_metrics against fixtures written by the reference's own src/metrics.py:81-134:
+    base k and a large k (13 of 20 items -> short rows; 40 > 32 -> the any-k exact kernel), with and without the
+    already-bought filter, and ragged hand-made lists with an empty one."""
+    meta, z = load_case(name)
+    mmeta, zm = load_case(name + '_metrics')
+    g = product_graph(grb, meta, z)
+    dev = torch.device('cuda:0')
+    h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    gt = (zm['gt_users'], zm['gt_items'])
+    eids = torch.from_numpy(zm['bought_eids'])
+    for kk in (mmeta['k'], mmeta['k_big']):
+        for rm in (True, False):
+            got = grb.get_metrics_at_k(h, g, None, meta['out'], gt, eids, kk, rm, True, dev)
+            np.testing.assert_allclose(got, zm['metrics/k%d/remove%d' % (kk, int(rm))], rtol=0, atol=1e-12)
+    lens, flat = zm['ragged/lens'], zm['ragged/items']
+    off = np.concatenate([[0], np.cumsum(lens)])
+    ragged = {int(u): flat[off[r]:off[r + 1]].tolist() for r, u in enumerate(zm['ragged/users'].tolist())}
+    truth = grb.create_ground_truth(*gt)
+    np.testing.assert_allclose(grb.recs_to_metrics(ragged, truth, g), zm['ragged/metrics'], rtol=0, atol=1e-12)
+
+
+def test_get_recs_any_k(grb):
+    """k > 32 (the reference's --k takes any value): ids == the oracle's argsort order for k = 33 and k = 100 > n_items / 2,
+    incl. rows that run out of items."""
+    meta, z = load_case('small_mean_128')
+    g = product_graph(grb, meta, z)
+    h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
+    buys = case_relations(z)[('user', 'buys', 'item')]
+    uids = z['user_ids'].tolist()[:64]
+    bought = grb.BoughtCSR.from_edges(buys[0], buys[1], meta['n_users'])
+    scores = O.get_recs_scores(h['user'], h['item'], uids).numpy()
+    for k in (33, 100, meta['n_items'] + 5):
+        ids = grb.get_recs_tensor(g, h, k, uids, bought, True, torch.device('cuda:0')).cpu().numpy().astype(np.int64)
+        want = O.get_recs_vectorised(h['user'], h['item'], k, np.asarray(uids), bought.indptr, bought.ids.astype(np.int64))
+        assert_topk_equivalent(ids, want, scores, k)
+    recs = grb.get_recs(g, h, None, meta['out'], 50, uids, {u: bought[u] for u in uids})
+    assert all(len(v) == 50 for v in recs.values())
+
+
+@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128'])
+def test_max_margin_loss_mask_and_recency_match_reference(grb, name):
+    """remove_false_negative / use_recency branches (src/model.py:516-531) on device score tensors vs the losses the
+    reference's own function produced (make_golden.py loss_case)."""
+    meta, z = load_case(name)
+    lmeta, zl = load_case(name + '_loss')
+    dev = torch.device('cuda:0')
+    pos, neg, mask = {}, {}, {}
+    for c in RELS:
+        if 'mask/%s' % c[1] in zl.files:
+            pos[c] = torch.from_numpy(z['pos/%s/score' % c[1]]).to(dev)
+            neg[c] = torch.from_numpy(z['neg/%s/score' % c[1]]).to(dev)
+            mask[c] = torch.from_numpy(zl['mask/%s' % c[1]])          # host tensors, as run.py:100-103 builds them
+    rec = {('user', 'buys', 'item'): torch.from_numpy(zl['recency/buys'])}
+    for rfn in (False, True):
+        for ur in (False, True):
+            got = grb.max_margin_loss(pos, neg, lmeta['delta'], lmeta['neg_k'], use_recency=ur, recency_scores=rec,
+                                      remove_false_negative=rfn, negative_mask=mask, cuda=True, device=dev)
+            np.testing.assert_allclose(float(got), float(zl['loss/mask%d/recency%d' % (int(rfn), int(ur))]), rtol=1e-5)
 
 
 @pytest.mark.parametrize('name', ['sport_mean_edge', 'sport_pool_nn'])
@@ -394,54 +458,92 @@ def clustered_embeddings(rng, n, d, spread):
     return torch.from_numpy(x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12))
 
 
-@pytest.mark.parametrize('cfg', [dict(elem='bf16', parts=2), dict(elem='fp16', parts=2), dict(elem='bf16', parts=1)],
-                         ids=['bf16x3', 'fp16x3', 'bf16x1'])
+@pytest.mark.parametrize('cfg', [dict(), dict(parts_users=2, parts_items=1), dict(elem='bf16', parts=2),
+                                 dict(elem='fp16', parts=2), dict(elem='bf16', parts=1)],
+                         ids=['fp16x1', 'fp16x2', 'bf16x3', 'fp16x3', 'bf16x1'])
 def test_quantised_scores_within_error_bound(grb, cfg):
-    """The soundness proof of the shortlist rests on |approx - exact| <= err_rel * max|y - c| + err_abs: check it."""
+    """The soundness proof of the shortlist rests on |approx - exact| <= err_u, computed from the MEASURED rounding
+    residuals of the operand rows (score_err in csrc/topk_aux.cu, mirrored by recs.score_err_bound): check it."""
     rng = np.random.default_rng(11)
     d, n_u, n_i = 128, 512, 4096
     hu, hi = clustered_embeddings(rng, n_u, d, 0.3).cuda(), clustered_embeddings(rng, n_i, d, 0.3).cuda()
-    c = grb.RecsConfig(shortlist=32, **cfg)
+    c = grb.RecsConfig(shortlist=32, k_band=False, **cfg)
     table = grb.ScoringTable(hi, c)
-    users_q, _ = grb.ops.score_prep(hu, None, table.d_pad, c.parts, c.elem_type, False)
-    sl_s, sl_i = grb.ops.score_topk_tc(users_q, table.items_q, 0, table.d_pad, c.parts, c.elem_type, None, None, 32)
+    users_q, ustats = grb.ops.score_prep(hu, None, table.d_pad, c.parts_users, c.elem_type, True)
+    sl_s, sl_i = grb.ops.score_topk_tc(users_q, table.items_q, 0, table.d_pad, c.parts_users, c.parts_items, c.elem_type,
+                                       None, None, 32)
     hu64, hi64 = hu.double().cpu(), hi.double().cpu()
     center = table.center.double().cpu()
     exact = hu64 @ (hi64 - center).t()
     got = torch.gather(exact, 1, sl_i.long().cpu())
     err = (got - sl_s.double().cpu()).abs().max().item()
-    bound = c.err_rel() * float(table.stats[0]) + c.err_abs(d)
+    ist, ust = table.stats.cpu().tolist(), ustats.cpu().tolist()
+    # the statistics are what they claim to be (fp64 recomputation of the residual norms)
+    q = table.items_q.view(torch.float16 if c.elem == 'fp16' else torch.bfloat16).double().cpu()
+    yc = torch.nn.functional.normalize(hi64, dim=1) - center
+    resid = yc - q[:, :d] - (q[:, 128:128 + d] if c.parts_items == 2 else 0)
+    # (+1e-7: the kernel rounds the fp32-normalised row, the fp64 recomputation the exactly normalised one; acc_err covers it)
+    assert abs(float(resid.norm(dim=1).max()) - ist[2]) <= 1e-3 * ist[2] + 1e-7
+    assert abs(float(yc.norm(dim=1).max()) - ist[0]) <= 1e-5
+    bound = grb.recs.score_err_bound(ust[2] * 1.001, ust[3] * 1.001, ist, c.elem, c.parts_users, c.parts_items, c.acc_err)
     assert err <= bound, (err, bound)
+    if c.products == 1 and c.elem == 'fp16':
+        assert bound < 6e-4  # what makes the single product usable as a first pass
     # and the shortlist really is the approximate top-32 (sorted, distinct)
     assert bool((sl_s[:, :-1] >= sl_s[:, 1:]).all())
     top = torch.topk(exact, 32, dim=1).values
     assert float((top[:, -1] - got.min(1).values).max()) <= 2 * bound
 
 
+def test_k_band_threshold_keeps_every_possible_top_k_item(grb):
+    """Epilogue rule max(S-th best, k-th best - band): whatever it drops lies more than `band` below the k-th best
+    approximate score, the kept entries are the exact approximate scores, and the first k entries equal the plain rule's."""
+    rng = np.random.default_rng(3)
+    d, n_u, n_i, k = 128, 300, 6000, 10
+    hu, hi = clustered_embeddings(rng, n_u, d, 0.3).cuda(), clustered_embeddings(rng, n_i, d, 0.3).cuda()
+    c = grb.RecsConfig()
+    table = grb.ScoringTable(hi, c)
+    users_q, ustats = grb.ops.score_prep(hu, None, table.d_pad, 1, c.elem_type, True)
+    band = grb.ops.score_band(table.stats, ustats, c.elem_type, 1, 1, c.acc_err)
+    plain_s, plain_i = grb.ops.score_topk_tc(users_q, table.items_q, 0, table.d_pad, 1, 1, c.elem_type, None, None, 32)
+    band_s, band_i = grb.ops.score_topk_tc(users_q, table.items_q, 0, table.d_pad, 1, 1, c.elem_type, None, None, 32, k, band)
+    b = float(band)
+    assert 0 < b < 2e-3
+    assert torch.equal(plain_s[:, :k], band_s[:, :k]) and torch.equal(plain_i[:, :k], band_i[:, :k])
+    tau_k = plain_s[:, k - 1:k]
+    must_keep = plain_s >= tau_k - b          # entries of the plain top-32 the band rule is not allowed to drop
+    for r in range(n_u):
+        kept = set(band_i[r][band_i[r] >= 0].tolist())
+        assert set(plain_i[r][must_keep[r]].tolist()) <= kept
+
+
 @pytest.mark.parametrize('pair', [1, 0], ids=['cta_pair', 'single_cta'])
 @pytest.mark.parametrize('shape', [(1000, 20000), (70000, 3000), (257, 129), (5, 40)])
 def test_recs_large_vs_exact_kernel_and_oracle(grb, shape, pair):
-    """Tensor-core path (both kernel variants) == brute-force fp32 kernel == oracle (vectorised) on clustered
-    embeddings with bought lists."""
-    lib = grb._native.load()
-    lib.gr_score_pair_mode(pair)
-    try:
-        _recs_large(grb, shape)
-    finally:
-        lib.gr_score_pair_mode(1)
+    """Tensor-core path (both kernel variants, tiered passes) == brute-force fp32 kernel == oracle (vectorised) on
+    clustered embeddings with bought lists."""
+    _recs_large(grb, shape, grb.RecsConfig(single_cta=not pair))
 
 
-def _recs_large(grb, shape):
+@pytest.mark.parametrize('cfg', [dict(shortlist=12), dict(shortlist=16, second=('fp16', 2, 1, 32)), dict(second=None, shortlist=10)],
+                         ids=['S12', 'second-2product', 'S10-nosecond'])
+def test_recs_tiers_are_exercised(grb, cfg):
+    """Small shortlists force users through pass 2 and the exact kernel: the answer must not depend on the route."""
+    n1, n2 = _recs_large(grb, (3000, 9000), grb.RecsConfig(**cfg), spread=0.02)
+    assert n1 > 0
+
+
+def _recs_large(grb, shape, cfg, spread=0.2):
     n_u, n_i = shape
     rng = np.random.default_rng(n_u)
     d, k = 128, 10
-    hu, hi = clustered_embeddings(rng, n_u, d, 0.2), clustered_embeddings(rng, n_i, d, 0.2)
+    hu, hi = clustered_embeddings(rng, n_u, d, spread), clustered_embeddings(rng, n_i, d, spread)
     nb = rng.integers(0, 6, n_u)
     bu = np.repeat(np.arange(n_u), nb)
     bi = rng.integers(0, n_i, bu.size)
     bought = grb.BoughtCSR.from_edges(bu, bi, n_u)
     dev = 'cuda:0'
-    table = grb.ScoringTable(hi.to(dev), grb.RecsConfig())
+    table = grb.ScoringTable(hi.to(dev), cfg)
     ids, sc, n_over = grb.recommend_topk(hu.to(dev), table, k, bought, return_overflow=True)
     ex_ids, ex_sc = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), grb.RecsConfig(exact_only=True)), k, bought)
     sample = np.arange(n_u) if n_u <= 2000 else rng.choice(n_u, 2000, replace=False)
@@ -452,7 +554,8 @@ def _recs_large(grb, shape):
     assert_topk_equivalent(ids.cpu().numpy()[sample].astype(np.int64), want, scores, k)
     for r in sample[:200]:
         assert not set(ids[r].tolist()) & set(bought[r])
-    assert int(n_over) <= n_u
+    assert n_over[1] <= n_over[0] <= n_u
+    return n_over
 
 
 def test_empty_inputs_and_empty_relations(grb):
@@ -499,14 +602,18 @@ def test_duplicate_items_overflow_path_and_fp16_never_overflows(grb):
     want = O.get_recs_vectorised(hu, hi, 10, np.arange(600))
     strict = grb.RecsConfig(elem='bf16', parts=2, tie_tol=0.0)
     ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), strict), 10, None, return_overflow=True)
-    assert int(n_over) == 600                                  # 100-fold ties: nothing can be proven at tolerance 0
+    assert n_over == (600, 600)                                # 100-fold ties: nothing can be proven at tolerance 0
     assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
     for elem in ('fp16', 'bf16'):
         cfg = grb.RecsConfig(elem=elem, parts=2)
         ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), cfg), 10, None, return_overflow=True)
         assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
         if elem == 'fp16':
-            assert int(n_over) == 0
+            assert n_over == (0, 0)
+    # the default tiers: the single fp16 product cannot prove a 100-fold tie, the fp16 3-product pass can
+    ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), grb.RecsConfig()), 10, None, return_overflow=True)
+    assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
+    assert n_over[0] > 0 and n_over[1] == 0
 
 
 # ------------------------------------------------------------------------------------------------ sampled blocks on the device

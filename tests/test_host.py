@@ -123,25 +123,35 @@ def test_bought_csr_forms_agree():
 
 
 def test_error_bound_arithmetic():
-    c = grb.RecsConfig(elem='bf16', parts=2, acc_err=0.0)
-    assert abs(c.err_rel() - 3 * 2.0 ** -18) < 1e-7
-    assert grb.RecsConfig(elem='fp16', parts=2, acc_err=0.0).err_rel() < 8e-7
-    assert grb.RecsConfig(elem='bf16', parts=1, acc_err=0.0).err_rel() > 3.9e-3
-    assert grb.RecsConfig(elem='fp16').err_abs(128) > 0 and grb.RecsConfig(elem='bf16').err_abs(128) == 0
-    # empirical check of the split-product bound on the CPU (bf16 hi/lo emulation)
+    """recs.score_err_bound (the host mirror of the device formula) really bounds the error of each product scheme,
+    emulated on the CPU with the measured residuals of the rounded rows."""
     g = torch.Generator().manual_seed(0)
     x = torch.nn.functional.normalize(torch.rand(256, 128, generator=g), dim=1)
     y = torch.nn.functional.normalize(torch.rand(512, 128, generator=g), dim=1)
     y = y - y.mean(0)
-
-    def split(v):
-        hi = v.to(torch.bfloat16).float()
-        return hi, (v - hi).to(torch.bfloat16).float()
-    xh, xl = split(x)
-    yh, yl = split(y)
-    approx = (xh.double() @ yh.double().t()) + (xl.double() @ yh.double().t()) + (xh.double() @ yl.double().t())
-    err = (approx - x.double() @ y.double().t()).abs().max().item()
-    assert err <= c.err_rel() * float(y.norm(dim=1).max())
+    exact = x.double() @ y.double().t()
+    for elem, dt in (('bf16', torch.bfloat16), ('fp16', torch.float16)):
+        def split(v):
+            hi = v.to(dt).float()
+            return hi, (v - hi).to(dt).float()
+        xh, xl = split(x)
+        yh, yl = split(y)
+        d = lambda a, b: a.double() @ b.double().t()
+        for pu, pi, approx in ((1, 1, d(xh, yh)), (2, 1, d(xh, yh) + d(xl, yh)), (2, 2, d(xh, yh) + d(xl, yh) + d(xh, yl))):
+            xr1, yr1 = (x - xh).norm(dim=1), (y - yh).norm(dim=1)
+            xr = xr1 if pu == 1 else (x - xh - xl).norm(dim=1)
+            yr = yr1 if pi == 1 else (y - yh - yl).norm(dim=1)
+            stats = [float(y.norm(dim=1).max()), 1.0, float(yr.max()), float(yr1.max())]
+            bound = grb.recs.score_err_bound(float(xr.max()), float(xr1.max()), stats, elem, pu, pi, 0.0)
+            err = (approx - exact).abs().max().item()
+            assert err <= bound, (elem, pu, pi, err, bound)
+            if (pu, pi) == (2, 2):
+                assert bound < (2e-5 if elem == 'bf16' else 1e-6)
+    c = grb.RecsConfig()
+    assert (c.elem, c.products, c.shortlist) == ('fp16', 1, 32) and c.second == ('fp16', 2, 2, 16)
+    assert grb.RecsConfig(parts=2, elem='bf16').products == 3 and grb.RecsConfig(parts=2).second is None
+    with pytest.raises(ValueError):
+        grb.RecsConfig(parts_users=1, parts_items=2)
 
 
 def test_unsupported_options_fail_loudly():

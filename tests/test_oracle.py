@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import EMBED_CASES, load_case, state_dict, case_relations, case_occurrence, assert_topk_equivalent
+from helpers import EMBED_CASES, load_case, state_dict, case_relations, case_occurrence, assert_topk_equivalent, RELS
 from oracle import straightline as O
 
 
@@ -101,6 +101,51 @@ def test_popularity_recs_match_reference(name):
     cos = O.get_recs_scores(hu, hi, uids).numpy()
     ratings = np.stack([O.softmax(r) for r in cos]) + zp['popularity'].reshape(1, -1) * pmeta['weight']
     assert_topk_equivalent(got, zp['recs_pop'], ratings, meta['k'], tol=1e-7)
+
+
+@pytest.mark.parametrize('name', ['tiny_mean', 'small_mean_128'])
+def test_metrics_match_reference(name):
+    """recs_to_metrics / get_metrics_at_k against fixtures written by the reference's own src/metrics.py:81-134
+    (make_golden.py metrics_case): k of the base case and a large k (13 of 20 items; 40 > 32), with and without the
+    already-bought filter, plus ragged hand-made recommendation lists with an empty one."""
+    meta, z = load_case(name)
+    mmeta, zm = load_case(name + '_metrics')
+    hu, hi = torch.from_numpy(z['emb/user']), torch.from_numpy(z['emb/item'])
+    g_users, g_items = zm['gt_users'], zm['gt_items']
+    truth = O.create_already_bought(g_users, g_items)          # same dict-of-lists shape as create_ground_truth
+    uids = np.unique(g_users).tolist()
+    buys = case_relations(z)[('user', 'buys', 'item')]
+    eids = zm['bought_eids']
+    bought = O.create_already_bought(buys[0][eids], buys[1][eids])
+    for kk in (mmeta['k'], mmeta['k_big']):
+        for rm in (True, False):
+            recs = O.get_recs(hu, hi, kk, uids, bought, remove_already_bought=rm)
+            got = O.recs_to_metrics({u: [int(i) for i in v] for u, v in recs.items()}, truth, meta['n_items'])
+            np.testing.assert_allclose(got, zm['metrics/k%d/remove%d' % (kk, int(rm))], rtol=0, atol=1e-12)
+    lens, flat = zm['ragged/lens'], zm['ragged/items']
+    off = np.concatenate([[0], np.cumsum(lens)])
+    ragged = {int(u): flat[off[r]:off[r + 1]].tolist() for r, u in enumerate(zm['ragged/users'].tolist())}
+    np.testing.assert_allclose(O.recs_to_metrics(ragged, truth, meta['n_items']), zm['ragged/metrics'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128'])
+def test_max_margin_loss_mask_and_recency_match_reference(name):
+    """remove_false_negative / use_recency branches of max_margin_loss (src/model.py:516-531) against losses computed by
+    the reference's own function (make_golden.py loss_case); recency exists for 'buys' only (the KeyError branch)."""
+    meta, z = load_case(name)
+    lmeta, zl = load_case(name + '_loss')
+    pos, neg, mask = {}, {}, {}
+    for c in RELS:
+        if 'mask/%s' % c[1] in zl.files:
+            pos[c], neg[c] = torch.from_numpy(z['pos/%s/score' % c[1]]), torch.from_numpy(z['neg/%s/score' % c[1]])
+            mask[c] = torch.from_numpy(zl['mask/%s' % c[1]])
+    rec = {('user', 'buys', 'item'): torch.from_numpy(zl['recency/buys'])}
+    for rfn in (False, True):
+        for ur in (False, True):
+            got = O.max_margin_loss(pos, neg, lmeta['delta'], lmeta['neg_k'], use_recency=ur, recency_scores=rec,
+                                    remove_false_negative=rfn, negative_mask=mask)
+            np.testing.assert_allclose(float(got), float(zl['loss/mask%d/recency%d' % (int(rfn), int(ur))]), rtol=1e-6)
+    assert float(zl['loss/mask1/recency1']) != float(zl['loss/mask0/recency0'])
 
 
 def test_recs_to_metrics_formula():

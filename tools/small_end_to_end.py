@@ -12,9 +12,8 @@ for agg, nl, hid in (('mean', 2, 128), ('pool_nn', 3, 256)):
     y = grb.get_embeddings(g, 128, model, loader, 1, True, dev, True)
     buys = data.relations()[('user', 'buys', 'item')]
     bought = grb.BoughtCSR.from_edges(buys[0], buys[1], 700)
-    for pair in (1, 0):
-        grb._native.load().gr_score_pair_mode(pair)
-        ids = grb.get_recs_tensor(g, y, 10, np.arange(700), bought, True, dev)
+    for single in (False, True):
+        ids = grb.get_recs_tensor(g, y, 10, np.arange(700), bought, True, dev, config=grb.RecsConfig(single_cta=single))
     ex = grb.recommend_topk(y['user'], grb.ScoringTable(y['item'], grb.RecsConfig(exact_only=True)), 10, bought)
     c = grb.metrics_from_tensor(ids, bought, 300)
 raw = torch.randint(0, 500, (5000,), device=dev)
