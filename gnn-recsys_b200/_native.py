@@ -54,7 +54,7 @@ SIGNATURES = {
     'gr_metrics_at_k': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gr_topk_merge': (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     'gr_csr_build_workspace_bytes': (_sz, [_i64, _i32]),
-    'gr_csr_build_i32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gr_csr_build_i32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gr_remap_workspace_bytes': (_sz, [_i64]),
     'gr_remap_first_appearance_i64': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gr_sample_key': (C.c_uint64, [C.c_uint64, C.c_uint64]),

@@ -145,13 +145,25 @@ __global__ void __launch_bounds__(THREADS) radix_scatter_kernel(const int* __res
   }
 }
 
+// status[0] |= 1 when some destination id lies outside [0, n_dst): the caller's input is invalid (the host twin
+// csr_by_dst_host raises IndexError for it). The build itself stays memory-safe for such input (csr_finish_kernel clamps).
+__global__ void csr_validate_kernel(const int* __restrict__ dst, long long nnz, int n_dst, int* __restrict__ status) {
+  bool bad = false;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
+    const int v = dst[j];
+    bad |= v < 0 || v >= n_dst;
+  }
+  if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
+}
+
 __global__ void csr_finish_kernel(const int* __restrict__ sorted_dst, const int* __restrict__ eperm,
                                   const int* __restrict__ src, long long nnz, int n_dst, int* __restrict__ indptr,
                                   int* __restrict__ indices) {
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
     indices[j] = src[eperm[j]];
-    const int kcur = sorted_dst[j];
-    const int kprev = j > 0 ? sorted_dst[j - 1] : -1;
+    // clamped: an out-of-range destination id (flagged by csr_validate_kernel) must never index outside indptr
+    const int kcur = min(max(sorted_dst[j], -1), n_dst - 1);
+    const int kprev = j > 0 ? min(max(sorted_dst[j - 1], -1), n_dst - 1) : -1;
     for (int v = kprev + 1; v <= kcur; ++v) indptr[v] = (int)j;
     if (j == nnz - 1)
       for (int v = kcur + 1; v <= n_dst; ++v) indptr[v] = (int)nnz;
@@ -190,11 +202,13 @@ extern "C" size_t gr_csr_build_workspace_bytes(int64_t nnz, int32_t n_dst) {
 }
 
 extern "C" int gr_csr_build_i32(const int32_t* src, const int32_t* dst, int64_t nnz, int32_t n_dst, int32_t* indptr,
-                                int32_t* indices, int32_t* eperm, void* ws, size_t ws_bytes, gr_stream_t stream) {
+                                int32_t* indices, int32_t* eperm, int32_t* status_or_null, void* ws, size_t ws_bytes,
+                                gr_stream_t stream) {
   GR_REQUIRE(nnz >= 0 && n_dst >= 0, GR_E_INVALID, "negative size");
   GR_REQUIRE(nnz <= 0x7fffffffLL, GR_E_INVALID, "int32 CSR cannot index more than 2^31 - 1 edges");
   GR_REQUIRE(indptr != nullptr, GR_E_INVALID, "null indptr");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (status_or_null != nullptr) GR_CUDA(cudaMemsetAsync(status_or_null, 0, sizeof(int32_t), st));
   if (nnz == 0) {
     fill_kernel<<<std::max(1, std::min((n_dst + 256) / 256, gr::sm_count() * 8)), 256, 0, st>>>(indptr, (long long)n_dst + 1, 0);
     GR_LAUNCH_CHECK();
@@ -212,6 +226,10 @@ extern "C" int gr_csr_build_i32(const int32_t* src, const int32_t* dst, int64_t 
   const int n_tiles = (int)((nnz + TILE - 1) / TILE);
   const int grid = std::min(n_tiles, gr::sm_count() * 8);
   const int passes = n_passes(n_dst);
+  if (status_or_null != nullptr) {
+    csr_validate_kernel<<<grid, THREADS, 0, st>>>(dst, nnz, n_dst, status_or_null);
+    GR_LAUNCH_CHECK();
+  }
   // ping-pong so that the last pass lands in (keys_?, eperm): vals alternate vals_b <-> eperm
   const int* kin = dst;
   const int* vin = nullptr;

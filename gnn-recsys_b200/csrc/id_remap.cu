@@ -13,7 +13,8 @@
 
 namespace {
 
-constexpr long long EMPTY = (long long)0x8000000000000000ull;  // INT64_MIN is reserved (not a valid raw id)
+constexpr long long EMPTY = (long long)0x8000000000000000ull;  // empty-slot marker; the raw id INT64_MIN itself is kept out
+//                                                                of the table and tracked in one dedicated word (`special`)
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -22,7 +23,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // 
   return x;
 }
 
-__global__ void table_init_kernel(long long* keys, int* vals, long long cap) {
+__global__ void table_init_kernel(long long* keys, int* vals, long long cap, int* special) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) special[0] = 0x7fffffff;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cap; i += (long long)gridDim.x * blockDim.x) {
     keys[i] = EMPTY;
     vals[i] = 0x7fffffff;
@@ -30,9 +32,13 @@ __global__ void table_init_kernel(long long* keys, int* vals, long long cap) {
 }
 
 __global__ void table_insert_kernel(const long long* __restrict__ raw, long long n, long long* keys, int* vals,
-                                    unsigned long long mask) {
+                                    unsigned long long mask, int* special) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long k = raw[i];
+    if (k == EMPTY) {  // the one raw id that collides with the empty-slot marker
+      atomicMin(special, (int)i);
+      continue;
+    }
     unsigned long long slot = mix64((unsigned long long)k) & mask;
     while (true) {
       const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
@@ -47,17 +53,18 @@ __global__ void table_insert_kernel(const long long* __restrict__ raw, long long
 }
 
 __device__ __forceinline__ int first_pos(const long long* __restrict__ keys, const int* __restrict__ vals,
-                                         unsigned long long mask, long long k) {
+                                         unsigned long long mask, long long k, const int* __restrict__ special) {
+  if (k == EMPTY) return special[0];
   unsigned long long slot = mix64((unsigned long long)k) & mask;
   while (keys[slot] != k) slot = (slot + 1) & mask;
   return vals[slot];
 }
 
 __global__ void flag_first_kernel(const long long* __restrict__ raw, long long n, const long long* __restrict__ keys,
-                                  const int* __restrict__ vals, unsigned long long mask, int* __restrict__ first,
-                                  int* __restrict__ flag) {
+                                  const int* __restrict__ vals, unsigned long long mask, const int* __restrict__ special,
+                                  int* __restrict__ first, int* __restrict__ flag) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int f = first_pos(keys, vals, mask, raw[i]);
+    const int f = first_pos(keys, vals, mask, raw[i], special);
     first[i] = f;
     flag[i] = f == (int)i ? 1 : 0;
   }
@@ -73,7 +80,7 @@ __global__ void assign_kernel(const long long* __restrict__ raw, long long n, co
   }
 }
 
-struct Layout { size_t keys, vals, first, rank, tiles, total; long long cap; };
+struct Layout { size_t keys, vals, first, rank, tiles, special, total; long long cap; };
 Layout layout(int64_t n) {
   Layout l;
   long long cap = 1024;
@@ -86,6 +93,7 @@ Layout layout(int64_t n) {
   l.first = take(4 * (size_t)std::max<int64_t>(n, 1));
   l.rank = take(4 * (size_t)std::max<int64_t>(n, 1));
   l.tiles = take(gr::scan_workspace_bytes(std::max<int64_t>(n, 1)));
+  l.special = take(256);
   l.total = off;
   return l;
 }
@@ -113,13 +121,14 @@ extern "C" int gr_remap_first_appearance_i64(const int64_t* raw, int64_t n, int3
   int* vals = reinterpret_cast<int*>(base + l.vals);
   int* first = reinterpret_cast<int*>(base + l.first);
   int* rank = reinterpret_cast<int*>(base + l.rank);
+  int* special = reinterpret_cast<int*>(base + l.special);
   const int grid = gr::sm_count() * 8;
   const unsigned long long mask = (unsigned long long)l.cap - 1;
-  table_init_kernel<<<grid, 256, 0, st>>>(keys, vals, l.cap);
+  table_init_kernel<<<grid, 256, 0, st>>>(keys, vals, l.cap, special);
   GR_LAUNCH_CHECK();
-  table_insert_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, keys, vals, mask);
+  table_insert_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, keys, vals, mask, special);
   GR_LAUNCH_CHECK();
-  flag_first_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, keys, vals, mask, first, rank);
+  flag_first_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, keys, vals, mask, special, first, rank);
   GR_LAUNCH_CHECK();
   GR_CUDA(gr::scan_exclusive_i32(rank, n, n_unique, reinterpret_cast<int*>(base + l.tiles), st));
   assign_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(raw), n, first, rank, new_ids,

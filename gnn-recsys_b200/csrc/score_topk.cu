@@ -82,6 +82,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// one lane of the (converged) warp; the operands of the tcgen05 instructions issued under it stay warp-uniform, so the
+// compiler keeps them in uniform registers instead of a per-instruction R2UR waterfall (the CUTLASS idiom)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -225,6 +238,36 @@ __device__ __noinline__ float coop_insert(float s, int gid, float* __restrict__ 
   return fmaxf(__shfl_sync(0xffffffffu, ne, S - 1), __shfl_sync(0xffffffffu, ne, kk - 1) - band);
 }
 
+// Four inserts into four DIFFERENT rows at once: the same instruction sequence, interleaved, so that the ~100-cycle
+// latency chain (LDS -> vote -> SHFL -> STS -> SHFL) of one insert hides behind the others. s.? == -inf marks an unused
+// slot (every lane compares >= it: position 32, nothing is stored). row.? = offset of the row in ls / li.
+__device__ __noinline__ float4 coop_insert4(float4 s4, int4 g4, int4 r4, float* __restrict__ ls, int* __restrict__ li,
+                                            int S, int kk, float band, int lane) {
+  const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+  const int g[4] = {g4.x, g4.y, g4.z, g4.w};
+  const int r[4] = {r4.x, r4.y, r4.z, r4.w};
+  float e[4], ne[4], nt[4];
+  int ei[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    e[i] = lane < S ? ls[r[i] + lane] : -INFINITY;
+    ei[i] = lane < S ? li[r[i] + lane] : -1;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = __popc(__ballot_sync(0xffffffffu, e[i] >= s[i]));
+    const float up = __shfl_up_sync(0xffffffffu, e[i], 1);
+    const int upi = __shfl_up_sync(0xffffffffu, ei[i], 1);
+    ne[i] = lane < pos ? e[i] : (lane == pos ? s[i] : up);
+    const int nei = lane < pos ? ei[i] : (lane == pos ? g[i] : upi);
+    if (lane >= pos && lane < S) { ls[r[i] + lane] = ne[i]; li[r[i] + lane] = nei; }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    nt[i] = fmaxf(__shfl_sync(0xffffffffu, ne[i], S - 1), __shfl_sync(0xffffffffu, ne[i], kk - 1) - band);
+  return make_float4(nt[0], nt[1], nt[2], nt[3]);
+}
+
 // Shared-memory plan: [A: UT x PA x KB sub-tiles][B ring: `ring` slots][shortlists][next-bought][barriers]
 constexpr int MAX_RING = 8;
 template <int KB, int PA, bool PAIR = false>
@@ -274,7 +317,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   uint64_t* t_empty = t_full + UT * 2;    // [UT][2]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + UT * 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler as well
+  const int lane = threadIdx.x & 31;
   const int n_tiles_all = (int)((n_items + TILE_N - 1) / TILE_N);
   const int tile0 = blockIdx.y * tiles_per_split;
   const int n_tiles = max(0, min(tiles_per_split, n_tiles_all - tile0));
@@ -335,7 +379,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
     // ================= MMA issuers: one thread per user tile (a single thread cannot issue the MMAs of both user
     // tiles fast enough to keep the tensor pipe busy: ~13 SASS instructions of descriptor traffic per MMA) ===========
     const int ut = warp == 1 ? 0 : 1;
-    if (lane == 0 && n_tiles > 0 && leader) {
+    if (n_tiles > 0 && leader) {
+      // The WHOLE warp walks the loop (barrier waits included); one elected lane issues. Everything the MMAs consume
+      // is warp-uniform: descriptors are built from uniform shared-memory offsets, the TMEM base is broadcast once.
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       mbar_wait(a_full, 0);
       tc_fence_after();
       int buf = 0;
@@ -343,21 +391,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       for (int j = 0; j < n_tiles; ++j) {
         const int slot = j & 1;
         const uint32_t aphase = (uint32_t)(j >> 1) & 1u;
+        const uint32_t d_tmem = tmem_u + (uint32_t)((ut * 2 + slot) * TILE_N);
         for (int pb = 0; pb < PB; ++pb) {
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(full + buf, phase);
+            if (pb == 0 && kb == 0) mbar_wait(t_empty + ut * 2 + slot, aphase ^ 1u);  // drained by the epilogue of tile j - 2
             tc_fence_after();
-            const uint64_t db = make_desc_sw128(smem_u32(sB + buf * SLOT));
-            {
-              const uint32_t d_tmem = tmem_base + (uint32_t)((ut * 2 + slot) * TILE_N);
-              if (pb == 0 && kb == 0) {  // accumulator slot must have been drained by the epilogue of tile j - 2
-                mbar_wait(t_empty + ut * 2 + slot, aphase ^ 1u);
-                tc_fence_after();
-              }
+            const uint64_t db = make_desc_sw128(sB_u + (uint32_t)(buf * SLOT));
+            if (elect_one()) {
               const int n_pa = pb == 0 ? PA : 1;
               for (int pa = 0; pa < n_pa; ++pa) {
-                const uint64_t da = make_desc_sw128(smem_u32(sA + ((ut * PA + pa) * KB + kb) * SUB_BYTES));
+                const uint64_t da = make_desc_sw128(sA_u + (uint32_t)(((ut * PA + pa) * KB + kb) * SUB_BYTES));
 #pragma unroll
                 for (int k = 0; k < KBLK / UMMA_K; ++k) {  // +32 bytes (>>4 = 2) per K = 16 step inside the swizzle atom
                   if (PAIR) tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
@@ -369,8 +414,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
               if (pb == PB - 1 && kb == KB - 1) {
                 if (PAIR) tc_commit_pair(t_full + ut * 2 + slot); else tc_commit(t_full + ut * 2 + slot);
               }
+              if (PAIR) tc_commit_pair(empty + buf); else tc_commit(empty + buf);
             }
-            if (PAIR) tc_commit_pair(empty + buf); else tc_commit(empty + buf);
+            __syncwarp();
             if (++buf == ring) { buf = 0; phase ^= 1u; }
           }
         }
@@ -455,11 +501,31 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
             uint32_t pend = __ballot_sync(0xffffffffu, gid >= 0);
             if (pend == 0) break;
             while (pend != 0) {
-              const int L = __ffs(pend) - 1;
+              const int L0 = __ffs(pend) - 1;
               pend &= pend - 1;
-              const float nt = coop_insert(__shfl_sync(0xffffffffu, s, L), __shfl_sync(0xffffffffu, gid, L),
-                                           ls + (t0 + L) * lst, li + (t0 + L) * lst, S, kk, band, lane);
-              if (lane == L) tau = nt;
+              if (pend == 0) {  // a single pending row
+                const float nt = coop_insert(__shfl_sync(0xffffffffu, s, L0), __shfl_sync(0xffffffffu, gid, L0),
+                                             ls + (t0 + L0) * lst, li + (t0 + L0) * lst, S, kk, band, lane);
+                if (lane == L0) tau = nt;
+              } else {          // up to four rows per call, interleaved
+                int L1 = __ffs(pend) - 1, L2 = -1, L3 = -1;
+                pend &= pend - 1;
+                if (pend != 0) { L2 = __ffs(pend) - 1; pend &= pend - 1; }
+                if (pend != 0) { L3 = __ffs(pend) - 1; pend &= pend - 1; }
+                float4 s4;
+                int4 g4, r4;
+                s4.x = __shfl_sync(0xffffffffu, s, L0); g4.x = __shfl_sync(0xffffffffu, gid, L0); r4.x = (t0 + L0) * lst;
+                s4.y = __shfl_sync(0xffffffffu, s, L1); g4.y = __shfl_sync(0xffffffffu, gid, L1); r4.y = (t0 + L1) * lst;
+                s4.z = L2 >= 0 ? __shfl_sync(0xffffffffu, s, L2 & 31) : -INFINITY;
+                g4.z = __shfl_sync(0xffffffffu, gid, L2 & 31); r4.z = (t0 + (L2 & 31)) * lst;
+                s4.w = L3 >= 0 ? __shfl_sync(0xffffffffu, s, L3 & 31) : -INFINITY;
+                g4.w = __shfl_sync(0xffffffffu, gid, L3 & 31); r4.w = (t0 + (L3 & 31)) * lst;
+                const float4 nt = coop_insert4(s4, g4, r4, ls, li, S, kk, band, lane);
+                if (lane == L0) tau = nt.x;
+                if (lane == L1) tau = nt.y;
+                if (lane == L2) tau = nt.z;
+                if (lane == L3) tau = nt.w;
+              }
             }
           }
         }

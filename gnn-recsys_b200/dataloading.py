@@ -83,6 +83,51 @@ def _draw_key(rng) -> int:
     return int(rng.integers(0, 2 ** 63, dtype=np.int64))
 
 
+AUTO = 'auto'
+_TORCH_LOADER_KWARGS = ('num_workers', 'pin_memory', 'collate_fn', 'persistent_workers', 'prefetch_factor', 'timeout',
+                        'worker_init_fn', 'generator', 'use_ddp', 'ddp_seed')  # accepted and ignored: no worker processes
+
+
+def resolve_edge_weight(g: HeteroGraph, edge_weight):
+    """DGL blocks carry the parent graph's edge frames, so ``graph.edata['occurrence']`` (read by the ``*_edge``
+    aggregators, ``src/model.py:174``) is there whenever the graph has it. ``'auto'`` (the loaders' default) mirrors
+    that: attach ``'occurrence'`` when any relation carries it. ``None`` attaches nothing, a name attaches that field."""
+    if edge_weight != AUTO:
+        return edge_weight
+    return 'occurrence' if any('occurrence' in g.edges[c].data for c in g.canonical_etypes) else None
+
+
+def _check_loader_kwargs(kind: str, kwargs):
+    unknown = [k for k in kwargs if k not in _TORCH_LOADER_KWARGS]
+    if unknown:
+        raise TypeError('%s got unexpected keyword argument(s) %s' % (kind, ', '.join(sorted(unknown))))
+
+
+class LazyFullBlock:
+    """Placeholder for the full-graph block of a loader in full-graph mode. ``get_embeddings`` swaps it for the
+    device-resident block (``HeteroGraph.full_block_on``) without ever building the HOST CSR (a stable argsort over
+    every edge list plus int64 copies: minutes and GBs at 500M edges, for a block nobody reads). Any other consumer
+    gets the real thing: ``.to(device)`` returns the device block, any other attribute materialises the host block."""
+
+    def __init__(self, g: HeteroGraph, edge_weight):
+        self._g, self._edge_weight, self._host = g, edge_weight, None
+
+    def to(self, device, *args, **kwargs):
+        if torch.device(device).type == 'cuda':
+            return self._g.full_block_on(torch.device(device), self._edge_weight)
+        return self.materialize()
+
+    def materialize(self) -> Block:
+        if self._host is None:
+            self._host = self._g.full_block(self._edge_weight)
+        return self._host
+
+    def __getattr__(self, name):
+        if name.startswith('_'):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
 class _FrontierSampler:
     """Shared block builder; subclasses choose which in-edges of the seeds form the frontier."""
 
@@ -124,11 +169,12 @@ class _FrontierSampler:
     def _fanout(self, layer: int):
         return None
 
-    def sample_blocks(self, g: HeteroGraph, seed_nodes, rng=None, exclude=None, edge_weight: Optional[str] = None,
+    def sample_blocks(self, g: HeteroGraph, seed_nodes, rng=None, exclude=None, edge_weight: Optional[str] = AUTO,
                       key: Optional[int] = None, device=None) -> List[Block]:
         """Blocks for ``seed_nodes``, innermost layer first. ``key`` (or one draw from ``rng``) fixes every random
         choice; ``device`` = a CUDA device builds the blocks there (``seed_nodes`` / ``exclude`` may then be device
-        tensors) with the same result."""
+        tensors) with the same result. ``edge_weight``: see ``resolve_edge_weight``."""
+        edge_weight = resolve_edge_weight(g, edge_weight)
         if key is None:
             key = _draw_key(rng if rng is not None else np.random.default_rng(0))
         if device is not None and torch.device(device).type == 'cuda':
@@ -207,19 +253,24 @@ class NodeDataLoader:
 
     With a full-neighbour sampler the embedding of a seed node does not depend on the batch it is computed in, so
     the loader takes the fast path whatever ``batch_size`` says (the reference passes 128, ``main_inference.py:134``):
-    ONE iteration whose blocks are full-graph blocks; ``get_embeddings`` then keeps only the seeded rows.
-    ``force_minibatch=True`` restores the reference's batching (sampled blocks per ``batch_size`` seeds) -- it only
-    differs when a mini-batch happens to contain no edge of some relation.
+    ONE iteration whose blocks are (lazy) full-graph blocks; ``get_embeddings`` then keeps only the seeded rows.
+    ``force_minibatch=True`` restores the reference's batching (sampled blocks per ``batch_size`` seeds).
+    KNOWN DIVERGENCE of the fast path (README, "Drop-in notes"): DGL's ``HeteroGraphConv`` skips a relation that has
+    no edge in the CURRENT mini-batch, which removes that relation's ``fc_self`` term for every node of the batch; in
+    one full-graph pass the relation is only skipped when the whole graph has no such edge. The two agree unless a
+    128-node batch happens to contain no edge of some relation -- an artefact of batching that
+    the golden case ``tiny_mean_batched`` reproduces with ``force_minibatch=True``.
     """
 
     def __init__(self, g: HeteroGraph, nids, block_sampler, batch_size=None, shuffle=False, drop_last=False,
-                 num_workers=0, seed=0, edge_weight=None, force_minibatch=False, device=None, **kwargs):
+                 seed=0, edge_weight=AUTO, force_minibatch=False, device=None, **kwargs):
+        _check_loader_kwargs('NodeDataLoader', kwargs)
         self.g, self.sampler = g, block_sampler
         self.device = device
         self.nids = {t: _as_np_ids(v).astype(np.int64) for t, v in nids.items()}
         self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
         self.rng = np.random.default_rng(seed)
-        self.edge_weight = edge_weight
+        self.edge_weight = resolve_edge_weight(g, edge_weight)
         self.force_minibatch = force_minibatch
         self._flat_t = np.concatenate([np.full(v.size, i) for i, (t, v) in enumerate(sorted(self.nids.items()))]) \
             if self.nids else np.zeros(0, np.int64)
@@ -239,7 +290,7 @@ class NodeDataLoader:
 
     def __iter__(self):
         if self.full_graph:
-            blk = self.g.full_block(self.edge_weight)
+            blk = LazyFullBlock(self.g, self.edge_weight)
             blocks = [blk] * self.sampler.num_layers
             ids = {t: torch.arange(self.g.num_nodes(t)) for t in self.g.ntypes}
             yield ids, {t: torch.from_numpy(v) for t, v in self.nids.items()}, blocks
@@ -295,11 +346,13 @@ class EdgeDataLoader:
     (same edge id) from the blocks."""
 
     def __init__(self, g: HeteroGraph, eids, block_sampler, g_sampling=None, exclude=None, reverse_etypes=None,
-                 negative_sampler=None, batch_size=1, shuffle=False, drop_last=False, num_workers=0, seed=0,
-                 pin_memory=False, device=None, **kwargs):
+                 negative_sampler=None, batch_size=1, shuffle=False, drop_last=False, seed=0, device=None,
+                 edge_weight=AUTO, **kwargs):
+        _check_loader_kwargs('EdgeDataLoader', kwargs)
         self.device = device
         self.g, self.g_sampling = g, (g_sampling if g_sampling is not None else g)
         self.sampler, self.neg = block_sampler, negative_sampler
+        self.edge_weight = resolve_edge_weight(self.g_sampling, edge_weight)  # blocks carry edata['occurrence'] like DGL's
         self.exclude, self.reverse_etypes = exclude, reverse_etypes or {}
         self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
         self.rng = np.random.default_rng(seed)
@@ -362,5 +415,6 @@ class EdgeDataLoader:
                     rc = g.to_canonical_etype(self.reverse_etypes[c[1]])
                     exclude[rc] = np.concatenate([exclude.get(rc, np.zeros(0, np.int64)), e])
             seeds = {t: v for t, v in space.items() if v.size}
-            blocks = self.sampler.sample_blocks(self.g_sampling, seeds, exclude=exclude, key=key)
+            blocks = self.sampler.sample_blocks(self.g_sampling, seeds, exclude=exclude, key=key,
+                                                edge_weight=self.edge_weight)
             yield ({t: blocks[0].srcnodes[t].data[NID] for t in blocks[0].srctypes}, pos_g, neg_g, blocks)

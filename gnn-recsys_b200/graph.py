@@ -228,7 +228,9 @@ class HeteroGraph:
             edges[tuple(c)] = (s, d)
         self._edges = dict(sorted(edges.items()))
         num = {}
-        for (st, _, dt), (s, d) in self._edges.items():
+        for (st, rn, dt), (s, d) in self._edges.items():
+            if s.size and (int(s.min()) < 0 or int(d.min()) < 0):  # DGL rejects these too; the int32 device CSR would wrap
+                raise ValueError('negative node id in relation %r' % ((st, rn, dt),))
             num[st] = max(num.get(st, 0), int(s.max()) + 1 if s.size else 0)
             num[dt] = max(num.get(dt, 0), int(d.max()) + 1 if d.size else 0)
         if num_nodes_dict:

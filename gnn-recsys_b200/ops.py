@@ -195,8 +195,10 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
     return out_s, out_i
 
 
-def csr_build(src: torch.Tensor, dst: torch.Tensor, n_dst: int):
-    """Stable COO -> CSR over destination rows on the device: ``(indptr, indices, eperm)``, all int32."""
+def csr_build(src: torch.Tensor, dst: torch.Tensor, n_dst: int, validate: bool = True):
+    """Stable COO -> CSR over destination rows on the device: ``(indptr, indices, eperm)``, all int32.
+    ``validate``: read back the device status word and raise ``IndexError`` for destination ids outside
+    ``[0, n_dst)`` like the host twin ``graph.csr_by_dst_host`` (one 4-byte D2H; ingest is not a hot path)."""
     assert src.dtype == torch.int32 and dst.dtype == torch.int32
     nnz = int(src.shape[0])
     dev = src.device
@@ -205,8 +207,11 @@ def csr_build(src: torch.Tensor, dst: torch.Tensor, n_dst: int):
     eperm = torch.empty(nnz, dtype=torch.int32, device=dev)
     lib = N.load()
     ws = N.workspace(lib.gr_csr_build_workspace_bytes(nnz, n_dst), dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev) if validate else None
     N.call('gr_csr_build_i32', N.ptr(src), N.ptr(dst), nnz, n_dst, N.ptr(indptr), N.ptr(indices), N.ptr(eperm),
-           N.ptr(ws), ws.numel(), N.stream())
+           N.ptr(status) if validate else None, N.ptr(ws), ws.numel(), N.stream())
+    if validate and int(status.item()) != 0:
+        raise IndexError('destination ids outside [0, %d)' % n_dst)
     return indptr, indices, eperm
 
 

@@ -177,5 +177,5 @@ def edge_batch_device(loader, items: Dict, key: int, device: torch.device):
             rc = g.to_canonical_etype(loader.reverse_etypes[c[1]])
             exclude[rc] = torch.cat([exclude[rc], e]) if rc in exclude else e
     seeds = {t: v for t, v in space.items() if v.numel()}
-    blocks = sample_blocks_device(loader.g_sampling, loader.sampler, seeds, key, device, exclude)
+    blocks = sample_blocks_device(loader.g_sampling, loader.sampler, seeds, key, device, exclude, loader.edge_weight)
     return ({t: blocks[0].srcnodes[t].data[NID] for t in blocks[0].srctypes}, pos_g, neg_g, blocks)

@@ -172,14 +172,17 @@ int gr_metrics_at_k(const int32_t* recs, int64_t n_users, int32_t k, const int64
  *      device, replacing what dgl.heterograph (src/builder.py:377-383) + DGL's lazy CSC build behind update_all do on
  *      the CPU. LSD radix sort of (dst, edge id): neighbours of a row stay in edge-id order (bit-exact against a
  *      stable argsort). eperm[j] = edge id stored in CSR slot j; indices[j] = src[eperm[j]]; indptr has n_dst + 1
- *      entries. src / dst are int32 device arrays with 0 <= dst < n_dst. */
+ *      entries. src / dst are int32 device arrays with 0 <= dst < n_dst; *status (optional device int32) is set to 0,
+ *      or to 1 when some dst lies outside that range (invalid input: the outputs are then unspecified, but the build
+ *      never writes out of bounds). */
 size_t gr_csr_build_workspace_bytes(int64_t nnz, int32_t n_dst);
 int gr_csr_build_i32(const int32_t* src, const int32_t* dst, int64_t nnz, int32_t n_dst, int32_t* indptr,
-                     int32_t* indices, int32_t* eperm, void* ws, size_t ws_bytes, gr_stream_t stream);
+                     int32_t* indices, int32_t* eperm, int32_t* status_or_null, void* ws, size_t ws_bytes,
+                     gr_stream_t stream);
 
 /* ---- ID remap next to the path: raw ids -> contiguous ids in order of FIRST APPEARANCE,
  *      replacing create_ids (src/builder.py:182-227: pandas unique() order + merge). new_ids[i] in [0, *n_unique);
- *      uniq_raw[new id] = raw id (optional reverse map, capacity n); n_unique is a device int32. INT64_MIN is not a
+ *      uniq_raw[new id] = raw id (optional reverse map, capacity n); n_unique is a device int32. Any int64 is a
  *      valid raw id. Deterministic (hash table keeps the smallest position per id) and bit-exact vs the CPU rule. */
 size_t gr_remap_workspace_bytes(int64_t n);
 int gr_remap_first_appearance_i64(const int64_t* raw, int64_t n, int32_t* new_ids, int64_t* uniq_raw_or_null,

@@ -1,0 +1,60 @@
+"""Experiment (CPU): how often does the scoring epilogue's slow path run on the real c2 score stream?
+
+Simulates the epilogue rule tile by tile (128 items, threshold frozen within a 32-column group) for 256 users = 8 warps
+of 32 rows, in item-id order, and reports per sweep: inserts per row, warp trips (32-column groups in which ANY lane has
+a candidate) and the number of lanes pending per trip -- the quantities that decide between a per-lane and a
+warp-cooperative insert.   usage: python tests/experiments/exp_insert_stream.py U I E
+"""
+import sys, os, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import gnn_recsys_b200 as grb
+from oracle import straightline as O
+torch.manual_seed(1)
+U, I, E = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+d = grb.make_graph(U, I, E, 0)
+num = {'user': U, 'item': I}
+blk = O.block_from_coo(num, num, {c: (s.astype(np.int64), t.astype(np.int64), None) for c, (s, t) in d.relations().items()})
+D = 128
+sd = {}
+for t, f in (('user', 2), ('item', 4)):
+    l = torch.nn.Linear(f, D)
+    sd['%s_embed.proj_feats.weight' % t] = l.weight.detach(); sd['%s_embed.proj_feats.bias' % t] = l.bias.detach()
+gain = torch.nn.init.calculate_gain('relu')
+for et in ('buys', 'bought-by', 'clicks', 'clicked-by'):
+    for nm in ('fc_self', 'fc_neigh'):
+        w = torch.empty(D, D); torch.nn.init.xavier_uniform_(w, gain=gain); sd['layers.0.mods.%s.%s.weight' % (et, nm)] = w
+y = O.get_embeddings_full(num, [blk], {'user': d.user_feat, 'item': d.item_feat}, sd, D)
+hu = torch.nn.functional.normalize(y['user'], dim=1); hi = torch.nn.functional.normalize(y['item'], dim=1)
+yc = (hi - hi.mean(0)).to(torch.float16).float()
+x = hu[:256].to(torch.float16).float()
+A = (x @ yc.t()).numpy()                     # [256, I] approximate scores, item-id order
+k = 10
+for S, band in ((32, 6.9e-4), (32, np.inf), (16, np.inf), (24, 6.9e-4)):
+    lists = np.full((256, S), -np.inf, dtype=np.float32)
+    tau = np.full(256, -np.inf, dtype=np.float32)
+    inserts = np.zeros(256, dtype=np.int64)
+    trips, lanes_hist = 0, np.zeros(33, dtype=np.int64)
+    for g0 in range(0, I, 32):
+        blk_s = A[:, g0:g0 + 32]
+        cand = blk_s > tau[:, None]
+        rows = cand.any(1)
+        for w in range(8):
+            n = int(rows[w * 32:(w + 1) * 32].sum())
+            if n:
+                trips += 1
+                lanes_hist[n] += 1
+        for r in np.nonzero(rows)[0]:
+            for sv in blk_s[r][cand[r]]:
+                if sv > tau[r]:
+                    l = lists[r]
+                    pos = int((l >= sv).sum())
+                    l[pos + 1:] = l[pos:-1]
+                    l[pos] = sv
+                    tau[r] = max(l[S - 1], l[k - 1] - band)
+                    inserts[r] += 1
+    groups = (I + 31) // 32
+    print('S=%d band=%s: inserts/row mean %.0f max %d; warp trips per warp-sweep %.0f of %d groups (%.1f per 128-item tile); '
+          'lanes pending per trip: mean %.2f, P(>=2) %.2f, P(>=4) %.2f, P(>=8) %.2f'
+          % (S, band, inserts.mean(), inserts.max(), trips / 8, groups, trips / 8 / (groups / 4),
+             (lanes_hist * np.arange(33)).sum() / max(trips, 1), lanes_hist[2:].sum() / max(trips, 1),
+             lanes_hist[4:].sum() / max(trips, 1), lanes_hist[8:].sum() / max(trips, 1)))

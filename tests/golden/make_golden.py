@@ -138,10 +138,13 @@ def embedding_case(name, n_users, n_items, n_edges, seed, n_layers, hidden, out,
 
 
 def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, batch, neg_k, aggregator='mean', full=False):
-    """Config-4 style training-step forward: sampled blocks + positive/negative edge scoring + loss."""
+    """Config-4 style training-step forward: sampled blocks + positive/negative edge scoring + loss. `_edge` aggregators:
+    the graph carries edata['occurrence'] and the loader's blocks pick it up like DGL's do (src/model.py:174)."""
     d = tiny_data(n_users, n_items, n_edges, seed)
-    g, _ = shim_graph(d)
+    g, occ = shim_graph(d, aggregator.endswith('_edge'), seed)
     pg = d.graph()
+    for et, v in occ.items():
+        pg.edges[et].data['occurrence'] = torch.from_numpy(v.astype(np.int64))
     torch.manual_seed(seed + 1)
     n_layers = len(fanouts) + 1
     model = ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, aggregator,
@@ -174,6 +177,8 @@ def forward_case(name, n_users, n_items, n_edges, seed, hidden, out, fanouts, ba
         for c, r in b.rels.items():
             arrays['block%d/indptr/%s' % (li, c[1])] = r.indptr
             arrays['block%d/indices/%s' % (li, c[1])] = r.indices
+            if r.weight is not None:
+                arrays['block%d/weight/%s' % (li, c[1])] = r.weight
     for t in pg.ntypes:
         arrays['feat/' + t] = blocks[0].srcnodes[t].data['features']
         arrays['h/' + t] = h[t]
@@ -303,6 +308,8 @@ def main_forward():
     forward_case('fwd_fanout_mean_128', 400, 150, 6000, seed=12, hidden=128, out=128, fanouts=[10, 10], batch=128, neg_k=50)
     forward_case('fwd_full_pool_nn', 300, 120, 5000, seed=13, hidden=128, out=64, fanouts=[0, 0], batch=64, neg_k=20,
                  aggregator='pool_nn', full=True)
+    forward_case('fwd_fanout_mean_edge', 300, 120, 5000, seed=14, hidden=32, out=16, fanouts=[10, 10], batch=64, neg_k=20,
+                 aggregator='mean_edge')
 
 
 def metrics_case(base_name, seed, k_big):

@@ -173,14 +173,27 @@ def test_metrics_match_reference_fixture(grb, name):
     h = {'user': torch.from_numpy(z['emb/user']), 'item': torch.from_numpy(z['emb/item'])}
     gt = (zm['gt_users'], zm['gt_items'])
     eids = torch.from_numpy(zm['bought_eids'])
+    truth = grb.create_ground_truth(*gt)
+    uids = np.unique(gt[0]).tolist()
+    buys = case_relations(z)[('user', 'buys', 'item')]
+    bought = O.create_already_bought(buys[0][zm['bought_eids']], buys[1][zm['bought_eids']])
     for kk in (mmeta['k'], mmeta['k_big']):
         for rm in (True, False):
+            want = zm['metrics/k%d/remove%d' % (kk, int(rm))]
+            # (1) the counting kernel on the oracle's recommendation lists (pinned to the reference in
+            #     tests/test_oracle.py): exactly the reference's numbers
+            recs = O.get_recs(h['user'], h['item'], kk, uids, bought, remove_already_bought=rm)
+            recs = {u: [int(i) for i in v] for u, v in recs.items()}
+            np.testing.assert_allclose(grb.recs_to_metrics(recs, truth, g), want, rtol=0, atol=1e-12)
+            # (2) the whole device pipeline: its lists may differ from the reference's where scores tie (< 1e-5), which
+            #     can move single hits -- a handful out of thousands of recommendations
             got = grb.get_metrics_at_k(h, g, None, meta['out'], gt, eids, kk, rm, True, dev)
-            np.testing.assert_allclose(got, zm['metrics/k%d/remove%d' % (kk, int(rm))], rtol=0, atol=1e-12)
+            n_rec = sum(len(v) for v in recs.values())
+            assert abs(got[0] - want[0]) <= 3.0 / n_rec and abs(got[1] - want[1]) <= 3.0 / len(gt[0])
+            assert abs(got[2] - want[2]) <= 3.0 / meta['n_items']
     lens, flat = zm['ragged/lens'], zm['ragged/items']
     off = np.concatenate([[0], np.cumsum(lens)])
     ragged = {int(u): flat[off[r]:off[r + 1]].tolist() for r, u in enumerate(zm['ragged/users'].tolist())}
-    truth = grb.create_ground_truth(*gt)
     np.testing.assert_allclose(grb.recs_to_metrics(ragged, truth, g), zm['ragged/metrics'], rtol=0, atol=1e-12)
 
 
@@ -252,7 +265,7 @@ def test_three_node_type_schema_matches_reference(grb, name):
     assert float(y['sport'].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128', 'fwd_full_pool_nn'])
+@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128', 'fwd_full_pool_nn', 'fwd_fanout_mean_edge'])
 def test_forward_scores_and_loss_match_reference(grb, name):
     meta, z = load_case(name)
     dev = torch.device('cuda:0')
@@ -262,9 +275,10 @@ def test_forward_scores_and_loss_match_reference(grb, name):
         nd = {t: int(z['block%d/ndst/%s' % (li, t)]) for t in ('user', 'item')}
         rels = {}
         for c in RELS:
+            wkey = 'block%d/weight/%s' % (li, c[1])
             rels[c] = grb.Relation(torch.from_numpy(z['block%d/indptr/%s' % (li, c[1])].astype(np.int32)),
                                    torch.from_numpy(z['block%d/indices/%s' % (li, c[1])].astype(np.int32)),
-                                   ns[c[0]], nd[c[2]])
+                                   ns[c[0]], nd[c[2]], None, torch.from_numpy(z[wkey]) if wkey in z.files else None)
         blocks.append(grb.Block(rels, ns, nd).to(dev))
     sizes = blocks[-1].num_dst
     pos_g = grb.edge_graph(sizes, {c: (z['pos/%s/src' % c[1]], z['pos/%s/dst' % c[1]]) for c in RELS})
@@ -525,19 +539,28 @@ def test_recs_large_vs_exact_kernel_and_oracle(grb, shape, pair):
     _recs_large(grb, shape, grb.RecsConfig(single_cta=not pair))
 
 
-@pytest.mark.parametrize('cfg', [dict(shortlist=12), dict(shortlist=16, second=('fp16', 2, 1, 32)), dict(second=None, shortlist=10)],
-                         ids=['S12', 'second-2product', 'S10-nosecond'])
+@pytest.mark.parametrize('cfg', [dict(shortlist=12), dict(shortlist=16, second=('fp16', 2, 1, 32)), dict(second=None, shortlist=10),
+                                 dict(elem='bf16', second=('bf16', 2, 2, 16))],
+                         ids=['S12', 'second-2product', 'S10-nosecond', 'bf16-tiers'])
 def test_recs_tiers_are_exercised(grb, cfg):
-    """Small shortlists force users through pass 2 and the exact kernel: the answer must not depend on the route."""
-    n1, n2 = _recs_large(grb, (3000, 9000), grb.RecsConfig(**cfg), spread=0.02)
-    assert n1 > 0
+    """Clusters of 30 near-duplicate items (1e-4 apart: inside the single-product error, far outside the 3-product
+    one) force users through pass 2 and, without one, the exact kernel: the answer must not depend on the route."""
+    rng = np.random.default_rng(17)
+    base = clustered_embeddings(rng, 300, 128, 0.2)
+    hi = base.repeat_interleave(30, dim=0) + 1e-4 * torch.from_numpy(rng.standard_normal((9000, 128)).astype(np.float32))
+    hi = torch.nn.functional.normalize(hi[torch.from_numpy(rng.permutation(9000))], dim=1).contiguous()
+    hu = clustered_embeddings(rng, 3000, 128, 0.2)
+    n1, n2 = _recs_large(grb, (3000, 9000), grb.RecsConfig(**cfg), tables=(hu, hi))
+    assert n1 > 1000
+    if cfg.get('second', True) is not None:
+        assert n2 < n1 // 10      # the second pass proves (nearly) everyone the first could not
 
 
-def _recs_large(grb, shape, cfg, spread=0.2):
+def _recs_large(grb, shape, cfg, tables=None):
     n_u, n_i = shape
     rng = np.random.default_rng(n_u)
     d, k = 128, 10
-    hu, hi = clustered_embeddings(rng, n_u, d, spread), clustered_embeddings(rng, n_i, d, spread)
+    hu, hi = tables if tables is not None else (clustered_embeddings(rng, n_u, d, 0.2), clustered_embeddings(rng, n_i, d, 0.2))
     nb = rng.integers(0, 6, n_u)
     bu = np.repeat(np.arange(n_u), nb)
     bi = rng.integers(0, n_i, bu.size)

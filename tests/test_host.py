@@ -107,6 +107,49 @@ def test_edge_loader_layout():
             assert int(np.diff(r.indptr.numpy()).max(initial=0)) <= 3
 
 
+def test_loaders_carry_occurrence_reject_unknown_kwargs_and_stay_lazy():
+    """Drop-in details of the loaders: (1) blocks carry the parent graph's edata['occurrence'] by default, like DGL's
+    (the `*_edge` aggregators read it, src/model.py:174), on the NodeDataLoader and the EdgeDataLoader; (2) unknown
+    keyword arguments raise instead of being swallowed, torch DataLoader's own are accepted; (3) a full-graph
+    NodeDataLoader hands out a lazy block: iterating it builds no host CSR."""
+    d, g = small_graph()
+    rng = np.random.default_rng(3)
+    occ = {}
+    for et, twin in (('buys', 'bought-by'), ('clicks', 'clicked-by')):
+        occ[et] = occ[twin] = torch.from_numpy(rng.integers(1, 5, g.num_edges(et)))
+    for et, v in occ.items():
+        g.edges[et].data['occurrence'] = v
+    eids = {'buys': np.arange(g.num_edges('buys')), 'clicks': np.arange(g.num_edges('clicks'))}
+    rev = {'buys': 'bought-by', 'bought-by': 'buys', 'clicks': 'clicked-by', 'clicked-by': 'clicks'}
+    loader = grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler([5, 5]), exclude='reverse_types', reverse_etypes=rev,
+                                negative_sampler=grb.negative_sampler.Uniform(3), batch_size=32, shuffle=True,
+                                num_workers=0, pin_memory=False)
+    assert loader.edge_weight == 'occurrence'
+    _, pos_g, neg_g, blocks = next(iter(loader))
+    for b in blocks:
+        for c, r in b.rels.items():
+            assert r.weight is not None and r.weight.dtype == torch.float32 and r.weight.shape[0] == r.nnz
+            assert torch.equal(r.weight, occ[c[1]][r.eperm.long()].float())   # the weight of the edge held by each CSR slot
+    off = grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler([5, 5]), batch_size=32, edge_weight=None)
+    assert all(r.weight is None for b in next(iter(off))[3] for r in b.rels.values())
+    nl = grb.NodeDataLoader(g, {'user': np.arange(60)}, grb.MultiLayerNeighborSampler([4]), batch_size=16)
+    assert all(r.weight is not None for r in next(iter(nl))[2][0].rels.values())
+    with pytest.raises(TypeError):
+        grb.EdgeDataLoader(g, eids, grb.MultiLayerNeighborSampler([5]), batch_size=8, edge_wieght='occurrence')
+    with pytest.raises(TypeError):
+        grb.NodeDataLoader(g, {'user': np.arange(60)}, grb.MultiLayerFullNeighborSampler(1), batchsize=8)
+    _, g2 = small_graph(seed=1)
+    assert grb.NodeDataLoader(g2, {'user': np.arange(60)}, grb.MultiLayerFullNeighborSampler(1)).edge_weight is None
+    full = grb.NodeDataLoader(g2, {'user': np.arange(60), 'item': np.arange(25)}, grb.MultiLayerFullNeighborSampler(2),
+                              batch_size=128, shuffle=True)
+    assert full.full_graph
+    (_, out_nodes, blks), = list(full)
+    assert len(blks) == 2 and not g2._csr_cache                 # nothing built on the host ...
+    assert blks[0].number_of_dst_nodes('user') == 60 and g2._csr_cache   # ... until somebody actually reads the block
+    with pytest.raises(ValueError):
+        grb.HeteroGraph({('user', 'buys', 'item'): (np.array([0, -1]), np.array([1, 1]))})
+
+
 def test_bought_csr_forms_agree():
     users = np.array([3, 1, 3, 0, 3, 1])
     items = np.array([9, 4, 2, 7, 9, 4])

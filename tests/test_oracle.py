@@ -48,7 +48,7 @@ def test_recs_match_reference(name):
     assert_topk_equivalent(vec, z['recs'], scores, meta['k'])
 
 
-@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128', 'fwd_full_pool_nn'])
+@pytest.mark.parametrize('name', ['fwd_fanout_mean', 'fwd_fanout_mean_128', 'fwd_full_pool_nn', 'fwd_fanout_mean_edge'])
 def test_forward_scores_and_loss_match_reference(name):
     meta, z = load_case(name)
     blocks = []
@@ -59,7 +59,8 @@ def test_forward_scores_and_loss_match_reference(name):
         for c in [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]:
             indptr, indices = z['block%d/indptr/%s' % (li, c[1])], z['block%d/indices/%s' % (li, c[1])]
             dst = np.repeat(np.arange(indptr.size - 1), np.diff(indptr))
-            rels[c] = (indices.astype(np.int64), dst, None)
+            wkey = 'block%d/weight/%s' % (li, c[1])
+            rels[c] = (indices.astype(np.int64), dst, z[wkey] if wkey in z.files else None)
         blocks.append(O.block_from_coo(ns, nd, rels))
     feats = {t: torch.from_numpy(z['feat/' + t]) for t in ('user', 'item')}
     cets = [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]
