@@ -108,10 +108,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_reference_sample(n_users, n_items, n_edges, d, budget_s=12.0, max_users=64, seed=0):
-    """Reference-semantics CPU path (oracle port) on a bounded sample, scaled to users/s of the whole job:
-    (a) layer-wise embedding pass on a c1-sized graph, scaled by edge count; (b) the per-user get_recs loop
-    (src/metrics.py:52-77) for a few users against a full-size item table."""
+def cpu_reference_sample(n_users, n_items, n_edges, d, budget_s=25.0, max_users=200, seed=0, vectorised=True):
+    """CPU baselines on a bounded sample, scaled to users/s of the whole job:
+    (a) layer-wise embedding pass (torch CPU index_add_ / scatter: already vectorised, like DGL's C++ SpMM) on a c1-sized
+        graph, scaled by edge count;
+    (b) REFERENCE semantics: the per-user get_recs loop of src/metrics.py:52-77 (oracle port) for up to `max_users` users
+        against a full-size item table -> `value`;
+    (c) FAIR vectorised path: blocked matmul + topk + bought filter (oracle.get_recs_vectorised) on all cores for a few
+        thousand users -> `vectorised`, so that the speed-up is not merely "Python loop removed"."""
     from oracle import straightline as O
     import gnn_recsys_b200 as grb
     torch.set_num_threads(os.cpu_count() or 1)
@@ -138,7 +142,8 @@ def cpu_reference_sample(n_users, n_items, n_edges, d, budget_s=12.0, max_users=
     reps = (n_items + si - 1) // si
     h_item = y['item'].repeat(reps, 1)[:n_items].contiguous()
     h_user = y['user']
-    bought = O.create_already_bought(data.relations()[('user', 'buys', 'item')][0], data.relations()[('user', 'buys', 'item')][1])
+    buys = data.relations()[('user', 'buys', 'item')]
+    bought = O.create_already_bought(buys[0], buys[1])
     done, t_recs = 0, 0.0
     while done < max_users and t_recs < budget_s:
         t0 = time.perf_counter()
@@ -150,8 +155,20 @@ def cpu_reference_sample(n_users, n_items, n_edges, d, budget_s=12.0, max_users=
     sample = ('oracle port of src/metrics.py:52-77 get_recs loop: %d users x %d items (%.3f s/user) + layer-wise CPU embedding '
               'pass on a %dx%dx%d graph (%.2f s) scaled by edge count to %.0f s; users/s = U / (t_embed + U * t_user)'
               % (done, n_items, per_user, su, si, se, t_embed_small, t_embed_est))
-    return dict(value=users_per_s, unit='users/s', cores=cores, kind='port', sample=sample, s_per_user=per_user,
-                embed_s_est=t_embed_est)
+    out = dict(value=users_per_s, unit='users/s', cores=cores, kind='port', sample=sample, s_per_user=per_user,
+               embed_s_est=t_embed_est)
+    if vectorised:  # (c)
+        bc = grb.BoughtCSR.from_edges(buys[0], buys[1], su)
+        nv = int(min(su, max(256, 2_000_000_000 // max(n_items, 1))))  # ~2e9 scores per timed call
+        uids = np.arange(nv)
+        O.get_recs_vectorised(h_user, h_item, K_RECS, uids[:64], bc.indptr, bc.ids.astype(np.int64))   # warm-up
+        t0 = time.perf_counter()
+        O.get_recs_vectorised(h_user, h_item, K_RECS, uids, bc.indptr, bc.ids.astype(np.int64))
+        t_vec = (time.perf_counter() - t0) / nv
+        out['vectorised'] = dict(value=n_users / (t_embed_est + n_users * t_vec), unit='users/s', cores=cores, s_per_user=t_vec,
+                                 sample='blocked torch matmul + topk + bought filter (oracle.get_recs_vectorised, all cores): '
+                                        '%d users x %d items (%.2e s/user) + the same embedding estimate' % (nv, n_items, t_vec))
+    return out
 
 
 def run_reference_arm(args, wl_name, wl):
@@ -163,7 +180,7 @@ def run_reference_arm(args, wl_name, wl):
     base = None
     t_start = time.perf_counter()
     for step in range(args.warmup + args.steps):
-        base = cpu_reference_sample(n_users, n_items, n_edges, out, budget_s=6.0, max_users=16, seed=step)
+        base = cpu_reference_sample(n_users, n_items, n_edges, out, budget_s=8.0, max_users=32, seed=step, vectorised=False)
         if step >= args.warmup:
             vals.append(base['value'])
     v = float(np.mean(vals))
@@ -187,8 +204,10 @@ def workload_config(name, wl, n_gpus, item_shards=None):
                                                                                  agg, hidden, out, K_RECS),
             'users': n_users, 'items': n_items, 'edges': n_edges, 'k': K_RECS,
             'parallelism': 'single GPU' if n_gpus == 1 else (
-                'dst/item id-range sharding x%d, NCCL all-gather + top-k merge' % n_gpus if item_shards != 1 else
-                'dst/user id-range sharding x%d, NCCL all-gather, replicated item table' % n_gpus),
+                ('contiguous id-range shards x%d: CSR rows, features and NodeEmbedding per rank, NCCL all-gather per layer; '
+                 'scoring: ' % n_gpus) +
+                ('item-range shards, per-shard top-k merged on the rank owning the user range (all-to-all)' if item_shards != 1
+                 else 'user-range shards against the all-gathered item table')),
             'l2': 'inputs larger than L2 (CSR + tables >> 126 MB per step), no explicit flush'}
 
 
@@ -367,6 +386,7 @@ def main():
     ap.add_argument('--neg-k', type=int, default=2500, help='c4: negatives per positive edge (reference default 2500)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true')
+    ap.add_argument('--one-layout', action='store_true', help='N>1: time only the primary scoring layout')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.config]
@@ -400,32 +420,68 @@ def main():
     t0 = time.perf_counter()
     data = grb.make_graph_device(n_users, n_items, n_edges, seed=0, device=dev)
     g = data.graph()
-    for t in g.ntypes:
-        g.nodes[t].data['features'] = g.nodes[t].data['features'].pin_memory()
+    num = {'user': n_users, 'item': n_items}
     t_gen = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    blk = g.full_block_on(dev)
-    torch.cuda.synchronize()
-    t_ingest = time.perf_counter() - t0
     torch.manual_seed(1)
     model = grb.ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': hidden, 'out': out}, True, 0.0, agg, 'cos',
                           'sum', True).to(dev).eval()
     n_conv = n_layers - 1
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    mem0 = torch.cuda.memory_allocated()
+    t0 = time.perf_counter()
+    if world == 1:
+        ranges = {t: (0, n) for t, n in num.items()}
+        blk = g.full_block_on(dev)
+    else:  # SHARDED STORAGE: this rank ingests and keeps only the CSR rows / feature rows of its destination id ranges
+        ranges = D.node_ranges(num, world, rank)
+        blk = g.sharded_block_on(dev, ranges)
+    torch.cuda.synchronize()
+    t_ingest = time.perf_counter() - t0
     blocks = [blk] * n_conv
+    feats_host = {t: g.nodes[t].data['features'][ranges[t][0]:ranges[t][1]].contiguous().pin_memory() for t in g.ntypes}
+    feats_dev = {t: v.to(dev) for t, v in feats_host.items()}
     buys = data.relations()[('user', 'buys', 'item')]
     bought = grb.BoughtCSR.from_edges(buys[0], buys[1], n_users)
     bought.on(dev)
+    graph_bytes = sum(r.indptr.numel() * 4 + r.indices.numel() * 4 + (r.eperm.numel() * 4 if r.eperm is not None else 0)
+                      for r in blk.rels.values())
+    resident = {'graph_csr_bytes': int(graph_bytes), 'feature_bytes': int(sum(v.numel() * 4 for v in feats_dev.values())),
+                'allocated_after_ingest_bytes': int(torch.cuda.memory_allocated() - mem0)}
     cfg = grb.RecsConfig(elem=args.elem, parts=args.parts, parts_users=args.parts_users, parts_items=args.parts_items,
                          shortlist=args.shortlist, k_band=not args.no_k_band)
-    feats_dev = {t: g.nodes[t].data['features'].to(dev) for t in g.ntypes}
     uid_all = np.arange(n_users)
+    layouts = ['single'] if world == 1 else (['user_shards', 'item_shards'] if args.item_shards == 1 else ['item_shards', 'user_shards'])
+    if args.one_layout:
+        layouts = layouts[:1]
+    own_range = {}  # layout -> user range whose recommendations this rank returns
 
-    stage_names = ['embed_in', 'aggregate', 'prep', 'score', 'rescore']
+    def forward_pass(layout, feats, mark):
+        """NodeEmbedding + conv layers. world > 1: own rows only, all-gather per layer (distributed.sharded_forward)."""
+        if world == 1:
+            h = model.embed(dict(feats))
+            mark('embed_in')
+            h = model.get_repr(blocks, h)
+            mark('aggregate')
+            return h
+        h = D.sharded_forward(model, blocks, feats, gather_last=('item',) if layout == 'user_shards' else ('user',), mark=mark)
+        mark('aggregate')
+        return h
 
-    own_range = [(0, n_users)]  # user range whose recommendations this rank returns
+    def score_pass(layout, h, mark):
+        if world == 1:
+            table = grb.ScoringTable(h['item'], cfg)
+            ids, scores, n_over = grb.recommend_topk(h['user'], table, K_RECS, bought, return_overflow=True, mark=mark)
+            own_range[layout] = (0, n_users)
+            return ids, n_over
+        ids, scores, owned, n_over = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark,
+                                                         item_shards=1 if layout == 'user_shards' else world,
+                                                         return_overflow=True)
+        own_range[layout] = owned
+        return ids, n_over
 
-    def resident_step(record=None):
-        """Inputs resident in HBM. Returns (ids, n_overflow); `record` collects CUDA events per stage."""
+    def resident_step(layout, record=None):
+        """Inputs resident in HBM. Returns (ids, n_overflow, h); `record` collects CUDA events per stage."""
         ev = {}
 
         def mark(name):
@@ -434,24 +490,8 @@ def main():
                 e.record()
                 ev[name] = e
         mark('t0')
-        h = {t: v for t, v in feats_dev.items()}
-        h = model.embed(h)
-        mark('embed_in')
-        if world == 1:
-            h = model.get_repr(blocks, h)
-        else:
-            h = D.sharded_get_repr(model, blocks, h, gather_last=('item',) if args.item_shards == 1 else None,
-                                   balance=('item',) if args.item_shards == 1 else ())
-        mark('aggregate')
-        if world == 1:
-            table = grb.ScoringTable(h['item'], cfg)
-            mark('prep0')
-            ids, scores, n_over = grb.recommend_topk(h['user'], table, K_RECS, bought, return_overflow=True, mark=mark)
-        else:
-            mark('prep0')
-            ids, scores, owned = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, mark=mark, item_shards=args.item_shards)
-            own_range[0] = owned
-            n_over = (0, 0)
+        h = forward_pass(layout, feats_dev, mark)
+        ids, n_over = score_pass(layout, h, mark)
         mark('t1')
         if record is not None:
             record.append(ev)
@@ -460,17 +500,19 @@ def main():
     loader = grb.NodeDataLoader(g, {'user': uid_all, 'item': np.arange(n_items)},
                                 grb.MultiLayerFullNeighborSampler(n_conv), batch_size=None)
     ids_pinned = torch.empty((D.chunk_rows(n_users, world), K_RECS), dtype=torch.int32).pin_memory()
+    if world == 1:
+        for t in g.ntypes:
+            g.nodes[t].data['features'] = feats_host[t]   # pinned: the public API copies them with non_blocking=True
 
-    def e2e_step():
-        """Public API with host features (pinned): H2D of the features and D2H of the id table inside the call."""
+    def e2e_step(layout):
+        """Public API with HOST features (pinned): H2D of the features and D2H of the id table inside the call."""
         if world == 1:
             y = grb.get_embeddings(g, out, model, loader, 1, True, dev, True)
             ids = grb.get_recs_tensor(g, y, K_RECS, uid_all, bought, True, dev, config=cfg)
         else:
-            h = {t: g.nodes[t].data['features'].to(dev, non_blocking=True) for t in g.ntypes}
-            h = D.sharded_get_repr(model, blocks, model.embed(h), gather_last=('item',) if args.item_shards == 1 else None,
-                                   balance=('item',) if args.item_shards == 1 else ())
-            ids, _, _ = D.sharded_recommend(h['user'], h['item'], K_RECS, bought, cfg, item_shards=args.item_shards)
+            feats = {t: v.to(dev, non_blocking=True) for t, v in feats_host.items()}   # this rank's rows only
+            h = forward_pass(layout, feats, lambda name: None)
+            ids, _ = score_pass(layout, h, None)
         host_ids = ids_pinned[:ids.shape[0]]
         host_ids.copy_(ids, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -481,79 +523,122 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_true(flag):
+        if world > 1:
+            t = torch.tensor([1.0 if flag else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item() > 0.5)
+        return bool(flag)
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
+
     # nvidia-smi starts BEFORE the warm-up: its start-up (NVML init) stalls kernel launches for milliseconds, which
     # must not land in the timed region (it showed up as a 6 ms "aggregate" stage on the 2 ms c1 step)
     sampler = ClockSampler(local) if rank == 0 else None
 
     # ---- warm-up (also the verification pass)
-    for _ in range(max(args.warmup, 1)):
-        ids, n_over, h = resident_step()
+    last = {}
+    for layout in layouts:
+        for _ in range(max(args.warmup, 1)):
+            last[layout] = resident_step(layout)
     barrier()
-    verified = None
+    resident['peak_allocated_bytes'] = int(torch.cuda.max_memory_allocated())
+    verified, verified_emb = {}, None
     if not args.no_verify:
-        # 512 sampled users of the range this rank owns, against the brute-force fp32 kernel over ALL items
-        ub, ue = own_range[0]
-        sample = torch.from_numpy(ub + np.random.default_rng(rank).choice(ue - ub, min(512, ue - ub), replace=False)).to(dev)
-        ex_tab = grb.ScoringTable(h['item'], grb.RecsConfig(exact_only=True))
-        ex_ids, ex_sc = grb.recommend_topk(h['user'][sample], ex_tab, K_RECS, bought.select(sample.cpu().numpy()))
-        hi_n = torch.nn.functional.normalize(h['item'], dim=1)
-        hu_n = torch.nn.functional.normalize(h['user'][sample], dim=1)
-        mine = ids[sample - ub]
-        s_got = (hu_n.unsqueeze(1) * hi_n[mine.long().clamp(min=0)]).sum(-1)
-        s_ex = (hu_n.unsqueeze(1) * hi_n[ex_ids.long().clamp(min=0)]).sum(-1)
-        verified = bool(((s_got - s_ex).abs() < 1e-5).all()) and bool(((mine < 0) == (ex_ids < 0)).all())
+        for layout in layouts:
+            ids, n_over, h = last[layout]
+            # 512 sampled users of the range this rank owns, against the brute-force fp32 kernel over ALL items
+            ub, ue = own_range[layout]
+            h_item_full = h['item']
+            if layout == 'item_shards':  # this layout never gathers the item table: do it here, for the checker only
+                h_item_full = D.allgather_rows(h['item'].clone(), n_items)
+            sample = torch.from_numpy(ub + np.random.default_rng(rank).choice(ue - ub, min(512, ue - ub), replace=False)).to(dev)
+            ex_tab = grb.ScoringTable(h_item_full, grb.RecsConfig(exact_only=True))
+            ex_ids, ex_sc = grb.recommend_topk(h['user'][sample], ex_tab, K_RECS, bought.select(sample.cpu().numpy()))
+            hi_n = torch.nn.functional.normalize(h_item_full, dim=1)
+            hu_n = torch.nn.functional.normalize(h['user'][sample], dim=1)
+            mine = ids[sample - ub]
+            s_got = (hu_n.unsqueeze(1) * hi_n[mine.long().clamp(min=0)]).sum(-1)
+            s_ex = (hu_n.unsqueeze(1) * hi_n[ex_ids.long().clamp(min=0)]).sum(-1)
+            ok = bool(((s_got - s_ex).abs() < 1e-5).all()) and bool(((mine < 0) == (ex_ids < 0)).all())
+            verified[layout] = all_true(ok)
         if world > 1:
-            t = torch.tensor([1.0 if verified else 0.0], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            verified = bool(t.item() > 0.5)
+            # sharded storage == the un-sharded pass: this rank's embedding rows (both node types) against
+            # model.get_repr over the FULL graph block, built here for the check only and dropped afterwards
+            h_sh = D.sharded_forward(model, blocks, feats_dev)
+            full_blk = g.full_block_on(dev)
+            feats_full = {t: g.nodes[t].data['features'].to(dev) for t in g.ntypes}
+            h_full = model.get_repr([full_blk] * n_conv, model.embed(feats_full))
+            ok = True
+            for t in ('user', 'item'):
+                b, e = ranges[t]
+                rows = torch.from_numpy(b + np.random.default_rng(rank + 7).choice(e - b, min(4096, e - b), replace=False)).to(dev)
+                other = torch.from_numpy(np.random.default_rng(rank + 9).choice(num[t], min(4096, num[t]), replace=False)).to(dev)
+                ok = ok and bool(torch.equal(h_sh[t][rows], h_full[t][rows])) and bool(torch.equal(h_sh[t][other], h_full[t][other]))
+            verified_emb = all_true(ok)
+            del h_sh, h_full, feats_full, full_blk
+            g._dev_blocks = {k_: v_ for k_, v_ in g._dev_blocks.items() if v_ is blk}
+            torch.cuda.empty_cache()
+    del last
 
-    # ---- timed: resident inputs, CUDA events, max over ranks
+    # ---- timed: resident inputs, CUDA events, max over ranks (primary layout = `value`; the other one after it)
+    timed = {}
     launches0 = N.kernel_launches()
-    rec = []
-    barrier()
-    w0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        ids, n_over, h = resident_step(rec)
-    ev1.record()
-    barrier()
-    w1 = time.perf_counter()
-    launches = N.kernel_launches() - launches0
-    clocks = sampler.stop(w0, w1) if sampler is not None else None
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = n_users / (ms_step * 1e-3)
+    clocks = None
+    for li, layout in enumerate(layouts):
+        rec = []
+        barrier()
+        w0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            ids, n_over, h = resident_step(layout, rec)
+        ev1.record()
+        barrier()
+        w1 = time.perf_counter()
+        if li == 0:
+            launches = N.kernel_launches() - launches0
+            clocks = sampler.stop(w0, w1) if sampler is not None else None
+        ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
 
-    def stage_ms(a, b):
-        return float(np.mean([e[a].elapsed_time(e[b]) for e in rec if a in e and b in e])) if rec and a in rec[0] and b in rec[0] else None
-    stages = {'embed_in_ms': stage_ms('t0', 'embed_in'), 'aggregate_ms': stage_ms('embed_in', 'aggregate'),
-              'prep_ms': stage_ms('aggregate', 'score_begin'), 'score_ms': stage_ms('score_begin', 'score_end'),
-              'rescore_ms': stage_ms('score_end', 'rescore_end'), 'second_pass_ms': stage_ms('rescore_end', 'fallback_end'),
-              'rescore_merge_ms': stage_ms('score_end', 't1')}
-    if world > 1:
-        stages['note'] = ('rank 0; aggregate_ms includes the per-layer NCCL all-gather, '
-                          'rescore_merge_ms the all-to-all + merge')
+        def stage_ms(a, b_, rec=rec):
+            ok = rec and a in rec[0] and b_ in rec[0]
+            return float(np.mean([e[a].elapsed_time(e[b_]) for e in rec])) if ok else None
+        stages = {'embed_in_ms': stage_ms('t0', 'embed_in'), 'aggregate_ms': stage_ms('embed_in', 'aggregate'),
+                  'prep_ms': stage_ms('aggregate', 'score_begin'), 'score_ms': stage_ms('score_begin', 'score_end'),
+                  'rescore_ms': stage_ms('score_end', 'rescore_end'), 'second_pass_ms': stage_ms('rescore_end', 'fallback_end'),
+                  'rescore_merge_ms': stage_ms('score_end', 't1')}
+        if world > 1:
+            comp = [stage_ms('embed_in' if i == 0 else 'gather%d' % (i - 1), 'compute%d' % i) for i in range(n_conv)]
+            gath = [stage_ms('compute%d' % i, 'gather%d' % i) for i in range(n_conv)]
+            stages['aggregate_kernels_ms'] = float(sum(comp)) if all(c is not None for c in comp) else None
+            stages['aggregate_allgather_ms'] = float(sum(gath)) if all(c is not None for c in gath) else None
+            stages['note'] = ('rank 0; embed_in_ms = NodeEmbedding of own rows + all-gather of the embedded inputs; aggregate_ms = '
+                              'kernels + per-layer NCCL all-gather; rescore_merge_ms includes the all-to-all + merge (item_shards)')
+        timed[layout] = dict(ms_step=ms_step, value=n_users / (ms_step * 1e-3), stages=stages, n_over=n_over)
+    primary = layouts[0]
+    ms_step, value, stages, n_over = (timed[primary][k_] for k_ in ('ms_step', 'value', 'stages', 'n_over'))
 
-    # ---- timed: end to end through the public API with host buffers
+    # ---- timed: end to end through the public API with host buffers (primary layout)
     for _ in range(min(args.warmup, 2)):
-        e2e_step()
+        e2e_step(primary)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ids_host = e2e_step()
+        ids_host = e2e_step(primary)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d = sum(int(g.nodes[t].data['features'].numel()) * 4 for t in g.ntypes)
-    d2h = int(ids_host.numel()) * 4
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    h2d = sum(int(v.numel()) * 4 for v in feats_host.values())   # this rank's feature rows ...
+    d2h = int(ids_host.numel()) * 4                              # ... and its users' id table
+    if world > 1:  # whole-job bytes: summed over the ranks
+        t = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
 
     if rank != 0:
         if world > 1:
@@ -568,14 +653,19 @@ def main():
         agg_bytes += 2 * 4 * (n_dst + 1) + 4 * n_edges + 4 * D_ * n_edges + 4 * D_ * n_dst + 4 * out * n_dst
     agg_bytes *= n_conv
     roof_agg = None
-    if stages.get('aggregate_ms'):
-        gbs = agg_bytes / world / (stages['aggregate_ms'] * 1e-3) / 1e9
-        shard_note = '' if world == 1 else ", this rank's 1/%d of the rows, all-gather time included" % world
+    agg_ms = stages.get('aggregate_kernels_ms') if world > 1 else stages.get('aggregate_ms')
+    if agg_ms:
+        gbs = agg_bytes / world / (agg_ms * 1e-3) / 1e9
+        traffic = dram_traffic(args.config, 'aggregate') if world == 1 else None
         roof_agg = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm'],
-                    'traffic': dram_traffic(args.config, 'aggregate') if world == 1 else None,
-                    'algorithmic_bytes': agg_bytes // world, 'of': pk['source'], 'per': 'GPU',
-                    'note': 'all fused CSR gather-reduce + projection kernels of one step (4 relations%s); '
-                            'bytes = SURVEY 8d B_dst' % shard_note}
+                    'traffic': traffic, 'dram_gbs': (traffic / (agg_ms * 1e-3) / 1e9) if traffic else None,
+                    'algorithmic_bytes': agg_bytes // world, 'of': pk['source'], 'per': 'GPU', 'kernel_ms': agg_ms,
+                    'note': 'all fused CSR gather-reduce + projection kernels of one step (4 relations%s): kernel time only; '
+                            'achieved = ALGORITHMIC bytes (SURVEY 8d B_dst, neighbour rows counted per edge) / time; '
+                            'dram_gbs = measured DRAM bytes of the committed ncu capture / time (popular rows hit L2)'
+                            % ('' if world == 1 else ", this rank's 1/%d of the rows; the all-gather is in aggregate_allgather_ms" % world)}
+        if world > 1 and stages.get('aggregate_ms'):
+            roof_agg['with_allgather_gbs'] = agg_bytes / world / (stages['aggregate_ms'] * 1e-3) / 1e9
     flops = 2.0 * n_users * n_items * out
     roof = None
     if stages.get('score_ms'):
@@ -599,11 +689,15 @@ def main():
         'metric': 'users/sec for full-graph embed+top-10 recs', 'value': value, 'unit': 'users/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 embeddings + %s x%d-product tcgen05 scoring (f32 accumulate, exact f32 re-score + proof%s)' % (args.elem, cfg.products, ', 3-product second pass' if cfg.second else ''),
-        'data': 'synthetic', 'config': workload_config(args.config, wl, world, args.item_shards),
+        'data': 'synthetic', 'config': workload_config(args.config, wl, world, None if world == 1 else (1 if primary == 'user_shards' else world)),
         'e2e': {'value': n_users / e2e_s, 'unit': 'users/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_aggregation': roof_agg,
-        'cpu_baseline': cpu, 'stages_ms': stages, 'overflow_users': list(n_over), 'verified_vs_exact_fp32': verified,
+        'cpu_baseline': cpu, 'stages_ms': stages, 'overflow_users': list(n_over),
+        'verified_vs_exact_fp32': (all(verified.values()) if verified else None), 'verified_layouts': verified or None,
+        'verified_sharded_embeddings': verified_emb,
+        'layouts': {k_: {'users_per_s': v_['value'], 'ms_per_step': v_['ms_step'], 'stages_ms': v_['stages']} for k_, v_ in timed.items()},
+        'resident_per_rank': resident,
         'setup_s': {'generate': t_gen, 'ingest_csr_build': t_ingest},
     }
     print(json.dumps(line))

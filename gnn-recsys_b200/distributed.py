@@ -123,10 +123,13 @@ def exchange_topk(ids: torch.Tensor, scores: torch.Tensor, group=None) -> Tuple[
     if pad:
         ids = torch.cat([ids, ids.new_full((pad, k), -1)], 0)
         scores = torch.cat([scores, scores.new_full((pad, k), float('-inf'))], 0)
+    dev = ids.device
+    if dist.get_backend(group) == 'gloo' and ids.is_cuda:  # gloo routes through the host (tests: two ranks on one GPU)
+        ids, scores = ids.cpu(), scores.cpu()
     out_ids, out_scores = torch.empty_like(ids), torch.empty_like(scores)
     dist.all_to_all_single(out_ids, ids.contiguous(), group=group)
     dist.all_to_all_single(out_scores, scores.contiguous(), group=group)
-    return out_ids.view(world, c, k), out_scores.view(world, c, k), b, e
+    return out_ids.view(world, c, k).to(dev), out_scores.view(world, c, k).to(dev), b, e
 
 
 def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None, gather_last=None,
@@ -154,6 +157,79 @@ def sharded_get_repr(model, blocks, h: Dict[str, torch.Tensor], group=None, gath
     return h
 
 
+def allgather_inplace(buf: torch.Tensor, world: int, rank: int, group=None) -> torch.Tensor:
+    """``buf``: ``[world * chunk, d]`` whose rows ``[rank * chunk, (rank + 1) * chunk)`` this rank has filled; every other
+    chunk is received in place (no staging copy: the kernels wrote straight into the collective's buffer)."""
+    if world == 1:
+        return buf
+    c = buf.shape[0] // world
+    mine = buf[rank * c:(rank + 1) * c]
+    if dist.get_backend(group) == 'gloo':  # gloo has no all_gather_into_tensor
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous(), group=group)
+        for r, p in enumerate(parts):
+            if r != rank:
+                buf[r * c:(r + 1) * c].copy_(p)
+    else:
+        dist.all_gather_into_tensor(buf, mine, group=group)
+    return buf
+
+
+def node_ranges(num_nodes: Dict[str, int], world: int, rank: int) -> Dict[str, Tuple[int, int]]:
+    """Equal contiguous id ranges per node type: what a rank STORES (CSR rows, features) and computes."""
+    return {t: shard_range(n, world, rank) for t, n in num_nodes.items()}
+
+
+def sharded_forward(model, sblocks, feats_local: Dict[str, torch.Tensor], group=None, gather_last=None,
+                    mark=None) -> Dict[str, torch.Tensor]:
+    """Embedding pass with SHARDED STORAGE: ``sblocks`` are this rank's ``HeteroGraph.sharded_block_on`` blocks (one per
+    conv layer; equal ``shard_range`` rows), ``feats_local[t]`` the raw feature rows of this rank's id range of node type
+    ``t``. Each rank embeds its own rows (``NodeEmbedding``), the embedded inputs are all-gathered (the next layer
+    gathers arbitrary source rows), and every conv layer computes this rank's destination rows straight into the
+    all-gather buffer. Per-rank resident graph + features are ~1/world of the whole; the gathered ``[N, D]`` tables
+    are not (every rank reads all source rows). ``gather_last``: node types to all-gather after the LAST layer
+    (default all); a type left out comes back full-height with only this rank's rows valid. ``mark(name)`` (optional)
+    is called after the input embedding + its gather ('embed_in'), after every layer's kernels ('compute<i>') and after
+    every layer's all-gather ('gather<i>') -- bench.py separates kernel time from collective time with it.
+    ``relu(fc_preagg(h))`` of the ``*_nn`` aggregators runs on all source rows on every rank: gathering the projected
+    table instead would move more bytes over NVLink than the (tensor-core) projection costs."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ranges = sblocks[0].shard_ranges
+    num = sblocks[0].num_src
+    h = {}
+    for t, x in feats_local.items():
+        b, e = ranges[t]
+        c = chunk_rows(num[t], world)
+        own = model.embed_type(t, x)
+        buf = own.new_empty((world * c, own.shape[1]))
+        buf[rank * c:rank * c + (e - b)].copy_(own)
+        if e - b < c:
+            buf[rank * c + (e - b):(rank + 1) * c].zero_()
+        h[t] = allgather_inplace(buf, world, rank, group)[:num[t]]
+    mark = mark or (lambda name: None)
+    mark('embed_in')
+    for i, blk in enumerate(sblocks):
+        last = i == len(sblocks) - 1
+        layer = model.layers[i]
+        d_out = next(iter(layer.mods.values()))._out_feats
+        bufs = {}
+        for t in blk.dsttypes:
+            c = chunk_rows(num[t], world)
+            bufs[t] = h[next(iter(h))].new_empty((world * c, d_out))
+            b, e = ranges[t]
+            if e - b < c:
+                bufs[t][rank * c + (e - b):(rank + 1) * c].zero_()
+        out = layer(blk, h, out_buffers=bufs)
+        mark('compute%d' % i)
+        h = {}
+        for t, v in out.items():
+            if not (last and gather_last is not None and t not in gather_last):
+                allgather_inplace(bufs[t], world, rank, group)
+            h[t] = bufs[t][:num[t]]
+        mark('gather%d' % i)
+    return h
+
+
 def choose_item_shards(n_users: int, n_items: int, world: int) -> int:
     """Scoring layout: ``world`` = item-range shards + owner-side merge (every rank preps / re-scores ALL users);
     ``1`` = user-range shards against a replicated item table (every rank preps ALL items, no exchange).
@@ -162,7 +238,7 @@ def choose_item_shards(n_users: int, n_items: int, world: int) -> int:
 
 
 def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought=None, config=None, group=None,
-                      mark=None, item_shards: Optional[int] = None):
+                      mark=None, item_shards: Optional[int] = None, return_overflow: bool = False):
     """Sharded scoring. ``h_user`` / ``h_item`` are the full tables (every rank holds them after the last
     all-gather); ``bought`` rows follow ``h_user`` rows. Returns ``(ids [u_loc, k], scores, (begin, end))`` for the
     user range this rank owns.
@@ -171,7 +247,9 @@ def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought
     users against its range and the per-shard exact top-k lists are merged on the rank owning the user range.
     ``item_shards = 1``: every rank scores only its own contiguous user range against the whole (replicated) item
     table -- no exchange, and the per-user prep / re-score work is not repeated on every rank.
-    ``item_shards = None`` (default) picks by ``choose_item_shards`` (shard the longer side)."""
+    ``item_shards = None`` (default) picks by ``choose_item_shards`` (shard the longer side).
+    Only the rows a layout reads need to be valid: the user-range layout reads this rank's user rows and ALL item rows,
+    the item-range layout ALL user rows and this rank's item rows (``sharded_forward(gather_last=...)``)."""
     from . import ops
     from .recs import RecsConfig, ScoringTable, recommend_topk
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -187,15 +265,15 @@ def sharded_recommend(h_user: torch.Tensor, h_item: torch.Tensor, k: int, bought
             if (ub, ue) not in cache:
                 cache[(ub, ue)] = bought.select(range(ub, ue))
             sub = cache[(ub, ue)]
-        ids, scores = recommend_topk(h_user[ub:ue], table, k, sub, mark=mark)
-        return ids, scores, (ub, ue)
+        ids, scores, n_over = recommend_topk(h_user[ub:ue], table, k, sub, mark=mark, return_overflow=True)
+        return (ids, scores, (ub, ue), n_over) if return_overflow else (ids, scores, (ub, ue))
     if item_shards != world:
         raise ValueError('item_shards must be 1 or the world size')
     ib, ie = shard_range(h_item.shape[0], world, rank)
     table = ScoringTable(h_item[ib:ie], cfg, item_id_base=ib)
-    ids, scores = recommend_topk(h_user, table, k, bought, mark=mark)
+    ids, scores, n_over = recommend_topk(h_user, table, k, bought, mark=mark, return_overflow=True)
     all_ids, all_scores, ub, ue = exchange_topk(ids, scores, group)
-    if world == 1:
-        return ids, scores, (ub, ue)
-    m_scores, m_ids = ops.topk_merge(all_scores.contiguous(), all_ids.contiguous(), k)
-    return m_ids[:ue - ub], m_scores[:ue - ub], (ub, ue)
+    if world > 1:
+        m_scores, m_ids = ops.topk_merge(all_scores.contiguous(), all_ids.contiguous(), k)
+        ids, scores = m_ids[:ue - ub], m_scores[:ue - ub]
+    return (ids, scores, (ub, ue), n_over) if return_overflow else (ids, scores, (ub, ue))

@@ -379,6 +379,34 @@ class HeteroGraph:
             self._dev_blocks[key] = Block(rels, self._num, self._num)
         return self._dev_blocks[key]
 
+    def sharded_block_on(self, device, ranges: Dict[str, Tuple[int, int]], edge_weight: Optional[str] = None) -> Block:
+        """This rank's SHARD of the full-graph block (multi-GPU, ``distributed.py``): for every relation only the CSR
+        rows of the destination range ``ranges[dst ntype] = (begin, end)`` -- ``indptr`` has ``end - begin + 1``
+        entries and starts at 0, ``indices`` are GLOBAL source ids, ``eperm`` holds the global edge id of each slot.
+        Only this rank's edges travel to the device, so the resident graph is ~1/world of the full CSR
+        (``Block.shard_ranges`` marks the block; ``HeteroGraphConv`` then computes exactly those rows)."""
+        key = (str(device), edge_weight, tuple(sorted(ranges.items())))
+        if key not in self._dev_blocks:
+            from . import ops
+            rels = {}
+            for c, (s, d) in self._edges.items():
+                if s.shape[0] > INT32_MAX or max(self._num[c[0]], self._num[c[2]]) > INT32_MAX:
+                    raise OverflowError('int32 CSR cannot index relation %r' % (c,))
+                b, e = ranges[c[2]]
+                sel = np.nonzero((d >= b) & (d < e))[0]            # ascending edge ids: the stable order survives
+                src = torch.from_numpy(s[sel].astype(np.int32, copy=False)).to(device)
+                dst = torch.from_numpy((d[sel] - b).astype(np.int32, copy=False)).to(device)
+                indptr, indices, eperm = ops.csr_build(src, dst, e - b)
+                eid = torch.from_numpy(sel.astype(np.int64)).to(device)[eperm.long()]
+                w = None
+                if edge_weight is not None and edge_weight in self._edge_frames[c]:
+                    w = self._edge_frames[c][edge_weight].reshape(-1)[eid.cpu()].to(device).to(torch.float32).contiguous()
+                rels[c] = Relation(indptr, indices, self._num[c[0]], e - b, eid.to(torch.int32), w)
+            blk = Block(rels, self._num, self._num)
+            blk.shard_ranges = {t: (int(b), int(e)) for t, (b, e) in ranges.items()}
+            self._dev_blocks[key] = blk
+        return self._dev_blocks[key]
+
     def device_edges(self, etype, device):
         """(src, dst) of one relation as int32 device tensors (cached) -- what the edge-scoring kernel reads."""
         c = self.to_canonical_etype(etype)
@@ -464,6 +492,34 @@ class DeviceEdgeGraph:
     @property
     def edges(self):
         return _TypedIndex(self._edge_frames, self.to_canonical_etype)
+
+    def sharded_block_on(self, device, ranges: Dict[str, Tuple[int, int]], edge_weight: Optional[str] = None) -> Block:
+        """This rank's SHARD of the full-graph block (multi-GPU, ``distributed.py``): for every relation only the CSR
+        rows of the destination range ``ranges[dst ntype] = (begin, end)`` -- ``indptr`` has ``end - begin + 1``
+        entries and starts at 0, ``indices`` are GLOBAL source ids, ``eperm`` holds the global edge id of each slot.
+        Only this rank's edges travel to the device, so the resident graph is ~1/world of the full CSR
+        (``Block.shard_ranges`` marks the block; ``HeteroGraphConv`` then computes exactly those rows)."""
+        key = (str(device), edge_weight, tuple(sorted(ranges.items())))
+        if key not in self._dev_blocks:
+            from . import ops
+            rels = {}
+            for c, (s, d) in self._edges.items():
+                if s.shape[0] > INT32_MAX or max(self._num[c[0]], self._num[c[2]]) > INT32_MAX:
+                    raise OverflowError('int32 CSR cannot index relation %r' % (c,))
+                b, e = ranges[c[2]]
+                sel = np.nonzero((d >= b) & (d < e))[0]            # ascending edge ids: the stable order survives
+                src = torch.from_numpy(s[sel].astype(np.int32, copy=False)).to(device)
+                dst = torch.from_numpy((d[sel] - b).astype(np.int32, copy=False)).to(device)
+                indptr, indices, eperm = ops.csr_build(src, dst, e - b)
+                eid = torch.from_numpy(sel.astype(np.int64)).to(device)[eperm.long()]
+                w = None
+                if edge_weight is not None and edge_weight in self._edge_frames[c]:
+                    w = self._edge_frames[c][edge_weight].reshape(-1)[eid.cpu()].to(device).to(torch.float32).contiguous()
+                rels[c] = Relation(indptr, indices, self._num[c[0]], e - b, eid.to(torch.int32), w)
+            blk = Block(rels, self._num, self._num)
+            blk.shard_ranges = {t: (int(b), int(e)) for t, (b, e) in ranges.items()}
+            self._dev_blocks[key] = blk
+        return self._dev_blocks[key]
 
     def device_edges(self, etype, device):
         u, v = self._edges[self.to_canonical_etype(etype)]

@@ -121,9 +121,15 @@ class HeteroGraphConv(nn.Module):
             raise KeyError(aggregate)
         self.aggregate = aggregate
 
-    def forward(self, g, inputs, row_ranges=None):
+    def forward(self, g, inputs, row_ranges=None, out_buffers=None):
         """``row_ranges`` (optional): ``{dst ntype: (begin, end)}`` -- compute only that destination shard
-        (multi-GPU); rows outside it are left untouched in the returned (full-height) tensors."""
+        (multi-GPU); rows outside it are left untouched in the returned (full-height) tensors. A block built by
+        ``HeteroGraph.sharded_block_on`` (``g.shard_ranges``) holds only this rank's CSR rows: its ranges are used and
+        the kernels walk the local ``indptr`` from 0. ``out_buffers`` (optional ``{dst ntype: [rows >= n, d_out]}``):
+        write into these tensors (e.g. an all-gather buffer) instead of allocating."""
+        shard = getattr(g, 'shard_ranges', None)
+        if shard is not None:
+            row_ranges = shard
         dst_inputs = {k: v[:g.number_of_dst_nodes(k)] for k, v in inputs.items()}
         todo: Dict[str, list] = {}
         for c in g.canonical_etypes:
@@ -133,14 +139,23 @@ class HeteroGraphConv(nn.Module):
             todo.setdefault(c[2], []).append(c)
         rsts = {}
         for dtype, cs in todo.items():
-            out = None
+            out = None if out_buffers is None else out_buffers.get(dtype)
             for i, c in enumerate(cs):
                 last = i == len(cs) - 1
                 acc = N.ACC_STORE if i == 0 else (N.ACC_MAX if self.aggregate == 'max' else N.ACC_ADD)
                 scale = 1.0 / len(cs) if (self.aggregate == 'mean' and last) else 1.0
                 rb, re = (0, None) if row_ranges is None else row_ranges[dtype]
-                out = self.mods[c[1]](g.rels[c], (inputs[c[0]], dst_inputs[dtype]), cetype=c, out=out,
-                                      accumulate=acc, z_scale=scale, row_begin=rb, row_end=re)
+                mod = self.mods[c[1]]
+                if shard is None:
+                    out = mod(g.rels[c], (inputs[c[0]], dst_inputs[dtype]), cetype=c, out=out, accumulate=acc,
+                              z_scale=scale, row_begin=rb, row_end=re)
+                else:  # local CSR rows [0, re - rb) <-> global destination rows [rb, re): views of the full tables
+                    if out is None:
+                        out = torch.empty((dst_inputs[dtype].shape[0], mod._out_feats), dtype=torch.float32,
+                                          device=dst_inputs[dtype].device)
+                    if re > rb:
+                        mod(g.rels[c], (inputs[c[0]], dst_inputs[dtype][rb:re]), cetype=c, out=out[rb:re],
+                            accumulate=acc, z_scale=scale)
             rsts[dtype] = out
         return rsts
 
@@ -196,6 +211,10 @@ class ConvModel(nn.Module):
         for i in range(len(blocks)):
             h = self.layers[i](blocks[i], h) if row_ranges is None else self.layers[i](blocks[i], h, row_ranges)
         return h
+
+    def embed_type(self, ntype: str, feats):
+        """NodeEmbedding of one node type's rows (any row subset: the multi-GPU path embeds each rank's own rows)."""
+        return getattr(self, ntype + '_embed')(feats)
 
     def embed(self, h):
         """NodeEmbedding per node type, in place in the passed dict like the reference (``model.py:462-466``)."""

@@ -26,7 +26,8 @@ for et in ('buys', 'bought-by', 'clicks', 'clicked-by'):
 y = O.get_embeddings_full(num, [blk], {'user': d.user_feat, 'item': d.item_feat}, sd, D)
 hu = torch.nn.functional.normalize(y['user'], dim=1); hi = torch.nn.functional.normalize(y['item'], dim=1)
 yc = (hi - hi.mean(0)).to(torch.float16).float()
-x = hu[:256].to(torch.float16).float()
+U0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+x = hu[U0:U0 + 256].to(torch.float16).float()
 A = (x @ yc.t()).numpy()                     # [256, I] approximate scores, item-id order
 k = 10
 for S, band in ((32, 6.9e-4), (32, np.inf), (16, np.inf), (24, 6.9e-4)):

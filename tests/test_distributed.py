@@ -58,6 +58,101 @@ def _worker(rank, world, port, n_users, n_items, k, ret):
         dist.destroy_process_group()
 
 
+def _cpu_kernels(grb):
+    """Stand-ins for the three C-ABI calls the embedding pass makes, in plain torch on the CPU (oracle semantics), so
+    that the SHARDING logic around them (local CSR rows, row ranges, all-gather buffers) can run under gloo."""
+    ops = grb.ops
+
+    def csr_build(src, dst, n_dst, validate=True):
+        a = O.csr_by_dst(src.numpy().astype(np.int64), dst.numpy().astype(np.int64), n_dst)
+        return tuple(torch.from_numpy(x) for x in a)
+
+    def linear(x, wt, bias=None, relu=False):
+        y = x.float() @ wt + (bias if bias is not None else 0)
+        return torch.relu(y) if relu else y
+
+    def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, out, reducer, l2norm, accumulate=0,
+                      z_scale=1.0, row_begin=0, row_end=None):
+        n = indptr.shape[0] - 1
+        row_end = n if row_end is None else row_end
+        deg = (indptr[1:] - indptr[:-1]).long()
+        dst = torch.repeat_interleave(torch.arange(n), deg)
+        msg = h_src[indices.long()] * (edge_w[:, None] if edge_w is not None else 1.0)
+        agg = torch.zeros(n, h_src.shape[1])
+        if reducer == grb._native.REDUCE_MAX:
+            agg = torch.full((n, h_src.shape[1]), float('-inf')).scatter_reduce(0, dst[:, None].expand_as(msg), msg, 'amax')
+            agg[deg == 0] = 0
+        else:
+            agg.index_add_(0, dst, msg)
+            agg = agg / deg.clamp(min=1)[:, None]
+        z = torch.relu(h_dst[:n] @ w_self_t + agg @ w_neigh_t)
+        if l2norm:
+            nrm = z.norm(dim=1, keepdim=True)
+            z = z / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+        r = slice(row_begin, row_end)
+        if accumulate == grb._native.ACC_ADD:
+            z = out[:n] + z
+        elif accumulate == grb._native.ACC_MAX:
+            z = torch.maximum(out[:n], z)
+        out[r] = (z * z_scale)[r]
+        return out
+
+    ops.csr_build, ops.linear, ops.sage_relation = csr_build, linear, sage_relation
+
+
+def _worker_sharded(rank, world, port, ret):
+    """sharded storage (HeteroGraph.sharded_block_on + distributed.sharded_forward) == the un-sharded pass, 3-layer
+    pool_nn and 2-layer mean with hetero 'mean', odd node counts (padded chunks, a short last shard)."""
+    import gnn_recsys_b200 as grb
+    D = grb.distributed
+    _cpu_kernels(grb)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        d = grb.make_graph(203, 77, 3000, seed=5)
+        g = d.graph()
+        num = {'user': 203, 'item': 77}
+        for n_layers, agg, hetero in ((3, 'pool_nn', 'sum'), (2, 'mean', 'mean')):
+            torch.manual_seed(7)
+            model = grb.ConvModel(g, n_layers, {'user': 2, 'item': 4, 'hidden': 16, 'out': 8}, True, 0.0, agg, 'cos', hetero).eval()
+            with torch.no_grad():
+                feats = {t: g.nodes[t].data['features'] for t in g.ntypes}
+                want = model.get_repr([g.full_block()] * (n_layers - 1), model.embed(dict(feats)))
+                ranges = D.node_ranges(num, world, rank)
+                sblk = g.sharded_block_on('cpu', ranges)
+                assert sblk.shard_ranges == ranges
+                for c, r in sblk.rels.items():
+                    b, e = ranges[c[2]]
+                    assert r.n_dst == e - b and r.indptr.shape[0] == e - b + 1 and int(r.indptr[0]) == 0
+                    full_ip = g.csr(c)[0]
+                    assert int(r.indptr[-1]) == int(full_ip[e] - full_ip[b])          # only this rank's edges are stored
+                    assert np.array_equal(r.eperm.numpy(), g.csr(c)[2][full_ip[b]:full_ip[e]])  # same stable slot order
+                local = {t: feats[t][ranges[t][0]:ranges[t][1]] for t in feats}
+                got = D.sharded_forward(model, [sblk] * (n_layers - 1), local)
+                for t in want:
+                    assert torch.allclose(got[t], want[t], rtol=1e-6, atol=1e-7), (t, agg)
+                part = D.sharded_forward(model, [sblk] * (n_layers - 1), local, gather_last=('item',))
+                ub, ue = ranges['user']
+                assert torch.allclose(part['user'][ub:ue], want['user'][ub:ue], rtol=1e-6, atol=1e-7)
+                assert torch.allclose(part['item'], want['item'], rtol=1e-6, atol=1e-7)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_sharded_storage_forward_equals_unsharded():
+    ctx = mp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: True, 1: True}
+
+
 def _run(world, n_users, n_items, k):
     ctx = mp.get_context('spawn')
     ret = ctx.Manager().dict()
