@@ -296,17 +296,42 @@ __global__ void __launch_bounds__(256, 2) linear_tc_kernel(const float* __restri
 
 }  // namespace
 
-extern "C" size_t gr_linear_workspace_bytes(int32_t d_in, int32_t d_out) {
-  if (d_in <= 0 || d_out <= 0) return 256;
+namespace gr {  // linear_tc5.cu: the tcgen05 path for the square bias-free projections (fc_preagg)
+bool linear_tc5_supported(int d_in, int d_out, bool has_bias);
+size_t linear_tc5_workspace_bytes(int64_t n, int d);
+int linear_tc5(const float* x, int64_t n, int d, const float* wt, int relu, float* y, void* ws, cudaStream_t st);
+}  // namespace gr
+
+static size_t legacy_workspace_bytes(int32_t d_in, int32_t d_out) {
   return gr::align_up((size_t)d_in * d_out * 2 * sizeof(float), 256);
 }
 
+constexpr int64_t TC5_MIN_ROWS = 256;  // below one row tile the three launches of the tcgen05 path are not worth it
+
+extern "C" size_t gr_linear_workspace_bytes(int64_t n, int32_t d_in, int32_t d_out) {
+  if (d_in <= 0 || d_out <= 0) return 256;
+  size_t need = legacy_workspace_bytes(d_in, d_out);
+  if (gr::linear_tc5_supported(d_in, d_out, false) && n >= TC5_MIN_ROWS)
+    need = std::max(need, gr::linear_tc5_workspace_bytes(n, d_in));
+  return need;
+}
+
 extern "C" int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const float* wt, const float* bias_or_null,
-                             int32_t d_out, int relu, float* y, void* ws, size_t ws_bytes, gr_stream_t stream) {
+                             int32_t d_out, int relu, int32_t flags, float* y, void* ws, size_t ws_bytes,
+                             gr_stream_t stream) {
   GR_REQUIRE(n >= 0 && d_in > 0 && d_out > 0, GR_E_INVALID, "bad shape");
   if (n == 0) return GR_OK;
   GR_REQUIRE(x && wt && y, GR_E_INVALID, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(flags & GR_LINEAR_FLAG_LEGACY) && gr::linear_tc5_supported(d_in, d_out, bias_or_null != nullptr) &&
+      n >= TC5_MIN_ROWS && ws != nullptr && ws_bytes >= gr::linear_tc5_workspace_bytes(n, d_in) &&
+      (reinterpret_cast<uintptr_t>(ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    int major = 0, dev = 0;
+    GR_CUDA(cudaGetDevice(&dev));
+    GR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major == 10) return gr::linear_tc5(x, n, d_in, wt, relu, y, ws, st);
+  }
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
   const bool reg_ok = d_out % 4 == 0 && d_out <= 1024 && 256 % (d_out / 4) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0 &&
@@ -320,7 +345,7 @@ extern "C" int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const floa
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)gr::sm_count() * 16);
     linear_small_kernel<<<grid, 256, 0, st>>>(x, n, d_in, wt, bias_or_null, d_out, relu, y);
   } else if (d_in % 8 == 0 && d_out % 32 == 0 && aligned && ws != nullptr &&
-             ws_bytes >= gr_linear_workspace_bytes(d_in, d_out) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+             ws_bytes >= legacy_workspace_bytes(d_in, d_out) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
     float4* packed = static_cast<float4*>(ws);
     const int total = d_in / 8 * (d_out / 8) * 32;
     pack_linear_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(wt, d_in, d_out, packed);

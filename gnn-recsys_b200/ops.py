@@ -30,16 +30,18 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
-    """``y = x @ wt (+ bias) (relu)`` with ``wt`` = ``nn.Linear.weight.t()`` ([d_in, d_out], contiguous)."""
+def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+           legacy: bool = False) -> torch.Tensor:
+    """``y = x @ wt (+ bias) (relu)`` with ``wt`` = ``nn.Linear.weight.t()`` ([d_in, d_out], contiguous).
+    ``legacy=True`` keeps the square bias-free shapes off the tcgen05 path (3xTF32 mma.sync instead; tests / experiments)."""
     x, wt = _f32(x), _f32(wt)
     n, d_in = x.shape
     d_out = wt.shape[1]
     assert wt.shape[0] == d_in
     y = torch.empty((n, d_out), dtype=torch.float32, device=x.device)
-    ws = _ws(N.load().gr_linear_workspace_bytes(d_in, d_out), x.device, 'linear')
+    ws = _ws(N.load().gr_linear_workspace_bytes(n, d_in, d_out), x.device, 'linear')
     N.call('gr_linear_f32', N.ptr(x), n, d_in, N.ptr(wt), N.ptr(_f32(bias)) if bias is not None else None, d_out,
-           int(relu), N.ptr(y), N.ptr(ws), ws.numel(), N.stream())
+           int(relu), N.LINEAR_FLAG_LEGACY if legacy else 0, N.ptr(y), N.ptr(ws), ws.numel(), N.stream())
     return y
 
 

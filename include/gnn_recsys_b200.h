@@ -47,12 +47,17 @@ int gr_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 /* ---- a1 NodeEmbedding.forward (src/model.py:19-24, nn.Linear with bias) and the pre-aggregation projection
  *      relu(fc_preagg(h)) of mean_nn / pool_nn (src/model.py:151,158; bias-free). Replaces torch addmm / cuBLAS sgemm.
  *      y[n, d_out] = x[n, d_in] . wt[d_in, d_out] (+ bias) (relu).  `wt` is the nn.Linear weight TRANSPOSED
- *      (k-major) so that output columns are contiguous. d_in <= 8: fp32 FFMA stream; d_in % 8 == 0 and d_out % 32 == 0
- *      with a workspace: 3xTF32 tensor-core GEMM (hi/lo split of both operands, fp32 accumulate: fp32-accurate);
- *      anything else: fp32 FFMA SGEMM. ws (gr_linear_workspace_bytes, 16-byte aligned) may be NULL (FFMA path). */
-size_t gr_linear_workspace_bytes(int32_t d_in, int32_t d_out);
+ *      (k-major) so that output columns are contiguous. Paths (all fp32-accurate):
+ *        d_in <= 8                                   fp32 FFMA stream (NodeEmbedding)
+ *        d_in == d_out in {128, 256}, no bias,       tcgen05 GEMM: fp16 hi/lo split of both operands with exact power-of-
+ *          n >= 256, workspace given                   two row / weight scaling, 3 products, fp32 accumulate in TMEM
+ *        d_in % 8 == 0, d_out % 32 == 0, workspace   3xTF32 mma.sync GEMM (also what GR_LINEAR_FLAG_LEGACY selects)
+ *        anything else                               fp32 FFMA SGEMM
+ *      ws (gr_linear_workspace_bytes(n, d_in, d_out), 256-byte aligned) may be NULL (FFMA paths only). */
+enum { GR_LINEAR_FLAG_LEGACY = 1 };
+size_t gr_linear_workspace_bytes(int64_t n, int32_t d_in, int32_t d_out);
 int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const float* wt, const float* bias_or_null,
-                  int32_t d_out, int relu, float* y, void* ws, size_t ws_bytes, gr_stream_t stream);
+                  int32_t d_out, int relu, int32_t flags, float* y, void* ws, size_t ws_bytes, gr_stream_t stream);
 
 /* ---- a3-a6 ConvLayer.forward for one relation, fused (src/model.py:123-237), replacing DGL update_all
  *      (libdgl SpMM copy_u/u_mul_e + mean/max), two torch sgemm, relu, norm/where/div and HeteroGraphConv's

@@ -1,23 +1,29 @@
-import sys, torch
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+"""gr_linear_f32 on the fc_preagg shapes: tcgen05 path vs the legacy 3xTF32 mma.sync path, time and max error vs fp64.
+
+    python tools/exp_linear.py [n_rows]
+"""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gnn_recsys_b200 as grb
-from gnn_recsys_b200 import ops, _native as N
+from gnn_recsys_b200 import ops
 dev = torch.device('cuda:0')
-for n, k, m in ((2_500_000, 256, 256), (1_000_000, 128, 128)):
-    x = torch.randn(n, k, device=dev); w = torch.randn(k, m, device=dev) * 0.1
-    def run(tc):
-        y = torch.empty(n, m, device=dev)
-        ws = ops._ws(N.load().gr_linear_workspace_bytes(k, m), dev, 'linear')
-        N.call('gr_linear_f32', N.ptr(x), n, k, N.ptr(w), None, m, 1, N.ptr(y), N.ptr(ws) if tc else None, ws.numel() if tc else 0, N.stream())
-        return y
-    for tc in (False, True):
-        for _ in range(2): y = run(tc)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_500_000
+g = torch.Generator(device=dev).manual_seed(0)
+for d in (128, 256):
+    x = torch.randn(n, d, device=dev, generator=g) * torch.exp(2 * torch.randn(n, 1, device=dev, generator=g))
+    w = torch.randn(d, d, device=dev, generator=g) * (2.0 / d) ** 0.5
+    wt = w.t().contiguous()
+    ref = torch.relu(x[:4096].double() @ wt.double())
+    for legacy in (False, True):
+        for _ in range(2):
+            y = ops.linear(x, wt, None, True, legacy=legacy)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5): y = run(tc)
+        for _ in range(5):
+            y = ops.linear(x, wt, None, True, legacy=legacy)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        ref = torch.relu(x[:4096].double() @ w.double())
-        err = (y[:4096].double() - ref).abs().max().item()
-        print('n=%d k=%d m=%d %s: %.2f ms  %.1f TFLOP/s  max abs err %.2e' % (n, k, m, '3xTF32' if tc else 'FFMA', ms, 2.0*n*k*m/ms/1e9, err))
+        err = ((y[:4096].double() - ref).abs() / (ref.abs() + 1e-5 * x[:4096].double().abs().amax(1, keepdim=True))).max().item()
+        print('d=%d n=%d %-8s %.3f ms  %.1f useful TFLOP/s  %.0f GB/s (8 D bytes/row)  max rel err %.2e'
+              % (d, n, 'legacy' if legacy else 'tcgen05', ms, 2.0 * n * d * d / ms / 1e9, 8.0 * d * n / ms / 1e6, err))
