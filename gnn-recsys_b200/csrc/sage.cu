@@ -738,8 +738,10 @@ __global__ void __launch_bounds__(THREADS, (VN == 1 && NT <= 4) ? 3 : 2) sage_fu
 }
 
 // ------------------------------------------------------------------------------------------------ generic dims
-// Any d_neigh / d_self / d_out <= 256 (e.g. raw 2/4-column features when embedding_layer=False): one warp per row,
-// scalar column loops, rows staged in shared memory. Correctness path for odd shapes, not a tuned kernel.
+// Any d_neigh / d_self / d_out <= 512 (e.g. raw 2/4-column features when embedding_layer=False, or the reference's
+// 192 / 384 / 512-wide presets, main.py:86-87): one warp per row, scalar column loops, rows staged in shared memory.
+// Correctness path for shapes the fused tile kernel does not cover, not a tuned kernel.
+constexpr int GEN_Q = 16;  // output columns per lane
 template <bool MAXR>
 __global__ void __launch_bounds__(128) sage_generic_kernel(SageParams p, LongWs lw) {
   extern __shared__ __align__(16) float smem[];
@@ -764,10 +766,10 @@ __global__ void __launch_bounds__(128) sage_generic_kernel(SageParams p, LongWs 
     }
     for (int c = lane; c < p.ds; c += 32) sRow[p.dn + c] = __ldg(p.h_dst + (size_t)row * p.ds + c);
     __syncwarp();
-    float z[8];
+    float z[GEN_Q];
     float ss = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < GEN_Q; ++q) {
       const int o = lane + 32 * q;
       z[q] = 0.f;
       if (o < p.dout) {
@@ -784,7 +786,7 @@ __global__ void __launch_bounds__(128) sage_generic_kernel(SageParams p, LongWs 
       if (nrm == 0.f) nrm = 1.f;
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < GEN_Q; ++q) {
       const int o = lane + 32 * q;
       if (o < p.dout) {
         float v = p.l2norm ? z[q] / nrm : z[q];
@@ -899,8 +901,8 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
                                     const float* w_neigh_t, int32_t d_out, int reducer, int l2norm, int accumulate,
                                     float z_scale, float* out, void* ws, size_t ws_bytes, gr_stream_t stream) {
   GR_REQUIRE(row_begin >= 0 && row_end >= row_begin, GR_E_INVALID, "bad row range");
-  GR_REQUIRE(d_neigh > 0 && d_self > 0 && d_out > 0 && d_neigh <= 256 && d_self <= 256 && d_out <= 256, GR_E_INVALID,
-             "dimensions must be in [1, 256]");
+  GR_REQUIRE(d_neigh > 0 && d_self > 0 && d_out > 0 && d_neigh <= 512 && d_self <= 512 && d_out <= 512, GR_E_INVALID,
+             "dimensions must be in [1, 512]");
   GR_REQUIRE(reducer == GR_REDUCE_MEAN || reducer == GR_REDUCE_MAX, GR_E_INVALID, "unknown reducer");
   GR_REQUIRE(accumulate >= GR_ACC_STORE && accumulate <= GR_ACC_MAX, GR_E_INVALID, "unknown accumulate mode");
   if (row_end == row_begin) return GR_OK;

@@ -514,7 +514,10 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
                                 const float* band_or_null, const int32_t* user_map_or_null, int32_t flags,
                                 float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes, gr_stream_t stream) {
   GR_REQUIRE(n_users >= 0 && n_items >= 0, GR_E_INVALID, "negative size");
-  GR_REQUIRE(d_pad == 64 || d_pad == 128, GR_E_INVALID, "d_pad must be 64 or 128 (pad the embeddings with gr_score_prep)");
+  GR_REQUIRE(d_pad == 64 || d_pad == 128 || d_pad == 192 || d_pad == 256, GR_E_INVALID,
+             "d_pad must be 64, 128, 192 or 256 (pad the embeddings with gr_score_prep)");
+  GR_REQUIRE(d_pad <= 128 || (parts_users == 1 && parts_items == 1), GR_E_INVALID,
+             "d_pad 192 / 256 (the reference's Large / Very Large out_dim presets) support the single-product scheme only");
   GR_REQUIRE((parts_users == 1 || parts_users == 2) && (parts_items == 1 || parts_items == 2) && parts_items <= parts_users,
              GR_E_INVALID, "(parts_users, parts_items) must be (1,1), (2,1) or (2,2)");
   GR_REQUIRE(elem_type == GR_ELEM_BF16 || elem_type == GR_ELEM_FP16, GR_E_INVALID, "unknown element type");
@@ -561,6 +564,8 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   }
   a.sl_score = part_score; a.sl_id = part_id;
   if (d_pad == 64) rc = launch_scheme<1, false>(a, parts_users, parts_items, st);
+  else if (d_pad == 192) rc = launch_score<3, 1, 1, true>(a, st);
+  else if (d_pad == 256) rc = launch_score<4, 1, 1, true>(a, st);
   else if (flags & GR_SCORE_FLAG_SINGLE_CTA) rc = launch_scheme<2, false>(a, parts_users, parts_items, st);
   else rc = launch_scheme<2, true>(a, parts_users, parts_items, st);  // CTA pairs (cta_group::2): the default
   if (rc != GR_OK) return rc;

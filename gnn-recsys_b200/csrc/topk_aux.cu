@@ -104,6 +104,8 @@ __device__ __forceinline__ void quantise(float w, int parts, int elem_type, uint
   r2 = fmaf(e2, e2, r2);
 }
 
+constexpr int PREP_MAXQ = 8;  // columns per lane: d_pad <= 256
+
 __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict__ x, long long n, int d,
                                                          const float* __restrict__ center, int d_pad, int parts,
                                                          int elem_type, uint16_t* __restrict__ out,
@@ -111,13 +113,13 @@ __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nq = d_pad / 32;  // 2 or 4
+  const int nq = d_pad / 32;  // 2, 4, 6 or 8
   float max_norm = 0.f, min_norm = INFINITY, max_r1 = 0.f, max_r2 = 0.f;
   for (long long r = warp; r < n; r += n_warps) {
-    float v[4];
+    float v[PREP_MAXQ];
     float ss = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < PREP_MAXQ; ++q) {
       const int c = lane + 32 * q;
       v[q] = (q < nq && c < d) ? __ldg(x + r * d + c) : 0.f;
       ss = fmaf(v[q], v[q], ss);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) score_prep_kernel(const float* __restrict
     float cs = 0.f, r1 = 0.f, r2 = 0.f;
     uint16_t* o = out + r * (long long)(parts * d_pad);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < PREP_MAXQ; ++q) {
       const int c = lane + 32 * q;
       if (q < nq) {
         float w = v[q] * inv;
@@ -602,7 +604,7 @@ extern "C" int gr_score_prep(const float* x, int64_t n, int32_t d, const float* 
                              int32_t parts, int32_t elem_type, uint16_t* out_q, float* stats4_or_null,
                              gr_stream_t stream) {
   GR_REQUIRE(n >= 0 && d > 0, GR_E_INVALID, "bad shape");
-  GR_REQUIRE(d_pad == 64 || d_pad == 128, GR_E_INVALID, "d_pad must be 64 or 128");
+  GR_REQUIRE(d_pad == 64 || d_pad == 128 || d_pad == 192 || d_pad == 256, GR_E_INVALID, "d_pad must be 64, 128, 192 or 256");
   GR_REQUIRE(d <= d_pad, GR_E_INVALID, "d exceeds d_pad");
   GR_REQUIRE(parts == 1 || parts == 2, GR_E_INVALID, "parts must be 1 or 2");
   GR_REQUIRE(elem_type == GR_ELEM_BF16 || elem_type == GR_ELEM_FP16, GR_E_INVALID, "unknown element type");

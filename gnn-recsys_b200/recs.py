@@ -162,11 +162,14 @@ class ScoringTable:
         self.h_item = h_item.contiguous()
         self.cfg, self.item_id_base = cfg, int(item_id_base)
         self.n_items, self.d = h_item.shape
-        self.tc = (not cfg.exact_only) and self.d <= 128 and self.n_items > 0
+        self.tc = (not cfg.exact_only) and self.d <= 256 and self.n_items > 0
         self.center, self.items_q, self.stats = None, None, None
         self._ops = {}
         if self.tc:
-            self.d_pad = 64 if self.d <= 64 else 128
+            self.d_pad = 64 * ((self.d + 63) // 64)
+            if self.d_pad > 128:  # out_dim 192 / 256 presets (main.py:86): single product only, no tensor-core second pass
+                from dataclasses import replace
+                self.cfg = cfg = replace(cfg, parts=None, parts_users=1, parts_items=1, second=None)
             if cfg.center:
                 self.center = ops.colmean_normalized(self.h_item)
             self.items_q, self.stats = self.operands(cfg.elem, cfg.parts_items)

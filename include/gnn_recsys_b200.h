@@ -97,7 +97,7 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *
  *  stage 0  gr_score_prep: rows are L2-normalised (x / max(|x|, 1e-12)), optionally shifted by `center`
  *           (the ranking per user is invariant to a common item shift; it shrinks the quantisation error bound),
- *           zero-padded to d_pad (64 or 128) and rounded to 16 bit (GR_ELEM_BF16 | GR_ELEM_FP16). parts == 2 stores a
+ *           zero-padded to d_pad (64, 128, 192 or 256; above 128 only the (1,1) scheme) and rounded to 16 bit (GR_ELEM_BF16 | GR_ELEM_FP16). parts == 2 stores a
  *           hi and a lo half per row ([hi d_pad | lo d_pad], x = hi + lo up to 2^-18 / 2^-22 relative).
  *           stats (float[4], caller-initialised {0, +inf, 0, 0}; atomic max / min over the rows):
  *             [0] max_i |row_i - center|            [1] smallest non-zero |x_i| (tells stage 2 when the eps clamp of

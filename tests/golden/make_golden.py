@@ -207,6 +207,10 @@ def main_embedding():
     # model-sized dims of configs c1/c2 (2-layer mean 128/128) and c3 (3-layer pool_nn hidden 256)
     embedding_case('small_mean_128', 400, 150, 6000, seed=9, n_layers=2, hidden=128, out=128, aggregator='mean')
     embedding_case('small_pool_256', 200, 80, 3000, seed=10, n_layers=3, hidden=256, out=128, aggregator='pool_nn')
+    # the other (hidden, out) presets of the reference's search space (main.py:86-87): Very Small, Small, Very Large
+    embedding_case('preset_64_32', 120, 50, 1500, seed=15, n_layers=3, hidden=64, out=32, aggregator='mean')
+    embedding_case('preset_192_96', 120, 50, 1500, seed=16, n_layers=3, hidden=192, out=96, aggregator='pool_nn')
+    embedding_case('preset_512_256', 100, 40, 1200, seed=17, n_layers=2, hidden=512, out=256, aggregator='mean')
 
 
 

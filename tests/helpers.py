@@ -12,7 +12,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 RELS = [('item', 'bought-by', 'user'), ('item', 'clicked-by', 'user'), ('user', 'buys', 'item'), ('user', 'clicks', 'item')]
 EMBED_CASES = ['tiny_mean', 'tiny_mean_nn', 'tiny_pool_nn', 'tiny_mean_edge', 'tiny_pool_nn_edge', 'tiny_mean_nonorm',
                'tiny_mean_noembed', 'tiny_pool_hetero_max', 'tiny_mean_hetero_mean', 'tiny_mean_batched',
-               'small_mean_128', 'small_pool_256']
+               'small_mean_128', 'small_pool_256', 'preset_64_32', 'preset_192_96', 'preset_512_256']
 
 
 def load_case(name):

@@ -83,7 +83,8 @@ RECS_CONFIGS = [dict(), dict(parts_users=2, parts_items=1), dict(k_band=False, s
 
 
 @pytest.mark.parametrize('cfg', RECS_CONFIGS, ids=lambda c: '-'.join('%s=%s' % kv for kv in c.items()))
-@pytest.mark.parametrize('name', ['tiny_mean', 'tiny_pool_nn', 'tiny_mean_nonorm', 'small_mean_128', 'small_pool_256'])
+@pytest.mark.parametrize('name', ['tiny_mean', 'tiny_pool_nn', 'tiny_mean_nonorm', 'small_mean_128', 'small_pool_256',
+                                  'preset_192_96', 'preset_512_256'])
 def test_recs_match_reference(grb, name, cfg):
     meta, z = load_case(name)
     dev = torch.device('cuda:0')
