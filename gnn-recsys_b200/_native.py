@@ -22,6 +22,7 @@ ELEM_BF16, ELEM_FP16 = 0, 1
 SCORE_MAX_SPLITS = 32
 SCORE_FLAG_SINGLE_CTA = 1
 LINEAR_FLAG_LEGACY = 1
+SAGE_FLAG_TF32_EPILOGUE = 1
 
 _i32, _i64, _f32, _sz, _vp = C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_void_p
 
@@ -34,9 +35,8 @@ SIGNATURES = {
     'gr_linear_workspace_bytes': (_sz, [_i64, _i32, _i32]),
     'gr_linear_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, C.c_int, _i32, _vp, _vp, _sz, _vp]),
     'gr_sage_relation_workspace_bytes': (_sz, [_i64, _i32]),
-    'gr_sage_epilogue_mode': (C.c_int, [C.c_int]),
     'gr_sage_relation_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _i32, C.c_int,
-                                       C.c_int, C.c_int, _f32, _vp, _vp, _sz, _vp]),
+                                       C.c_int, C.c_int, _f32, _i32, _vp, _vp, _sz, _vp]),
     'gr_gather_reduce_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, C.c_int, _vp, _vp, _sz, _vp]),
     'gr_edge_cosine_f32': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     'gr_colmean_workspace_bytes': (_sz, [_i64, _i32]),

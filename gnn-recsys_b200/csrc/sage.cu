@@ -20,7 +20,6 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
-#include <atomic>
 #include <cmath>
 
 #include "common.cuh"
@@ -881,15 +880,7 @@ bool fast_dims(int dn, int ds, int dout) {
 
 size_t packed_bytes(int dn, int ds, int dout) { return gr::align_up((size_t)(dn + ds) * dout * 2 * sizeof(float), 256) + 256; }
 
-// projection epilogue: 1 = fp16 split on m16n8k16 (default), 0 = tf32 split on m16n8k8
-std::atomic<int> g_epilogue_f16{1};
-
 }  // namespace
-
-extern "C" int gr_sage_epilogue_mode(int set_or_negative) {
-  if (set_or_negative >= 0) g_epilogue_f16.store(set_or_negative != 0 ? 1 : 0);
-  return g_epilogue_f16.load();
-}
 
 extern "C" size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh) {
   return long_ws_layout(nnz < 0 ? 0 : nnz, d_neigh, nullptr, nullptr) + packed_bytes(256, 256, 256);
@@ -899,7 +890,8 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
                                     int64_t nnz, const float* h_src, const float* h_dst, int64_t row_begin,
                                     int64_t row_end, int32_t d_neigh, int32_t d_self, const float* w_self_t,
                                     const float* w_neigh_t, int32_t d_out, int reducer, int l2norm, int accumulate,
-                                    float z_scale, float* out, void* ws, size_t ws_bytes, gr_stream_t stream) {
+                                    float z_scale, int32_t flags, float* out, void* ws, size_t ws_bytes,
+                                    gr_stream_t stream) {
   GR_REQUIRE(row_begin >= 0 && row_end >= row_begin, GR_E_INVALID, "bad row range");
   GR_REQUIRE(d_neigh > 0 && d_self > 0 && d_out > 0 && d_neigh <= 512 && d_self <= 512 && d_out <= 512, GR_E_INVALID,
              "dimensions must be in [1, 512]");
@@ -921,7 +913,7 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
     long_ws_layout(nnz, d_neigh, &lw, static_cast<char*>(ws));
     float* wscale = reinterpret_cast<float*>(static_cast<char*>(ws) + long_bytes);
     float4* packed = reinterpret_cast<float4*>(static_cast<char*>(ws) + long_bytes + 256);
-    const bool f16 = g_epilogue_f16.load() != 0 && d_neigh % 16 == 0 && d_self % 16 == 0;
+    const bool f16 = !(flags & GR_SAGE_FLAG_TF32_EPILOGUE) && d_neigh % 16 == 0 && d_self % 16 == 0;
     if (f16) {
       weight_scale_kernel<<<1, 1024, 0, st>>>(w_self_t, w_neigh_t, d_self * d_out, d_neigh * d_out, wscale);
       GR_LAUNCH_CHECK();

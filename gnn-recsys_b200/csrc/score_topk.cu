@@ -244,8 +244,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       }
     }
   } else if (warp == 1 || warp == MMA_WARP1) {
-    // ================= MMA issuers: one thread per user tile (a single thread cannot issue the MMAs of both user
-    // tiles fast enough to keep the tensor pipe busy: ~13 SASS instructions of descriptor traffic per MMA) ===========
+    // ================= MMA issuers (leader CTA), one warp per user tile. Why two warps: tcgen05.mma issue BLOCKS the
+    // issuing warp on the tensor pipe's queue (tools/exp_mma_issue.cu: one warp sustains 1 MMA per 85 cycles, the pipe
+    // wants 1 per 64; two warps reach 64). The WHOLE warp walks the loop (barrier waits included) and one elected lane
+    // issues: everything the MMAs consume is warp-uniform (descriptors from uniform shared-memory offsets, the TMEM
+    // base broadcast once), so UTCHMMA is fed from uniform registers -- four instructions for four MMAs. (With
+    // `if (lane == 0)` every MMA went through an 18-instruction R2UR waterfall.) =================
     const int ut = warp == 1 ? 0 : 1;
     if (n_tiles > 0 && leader) {
       // The WHOLE warp walks the loop (barrier waits included); one elected lane issues. Everything the MMAs consume

@@ -46,7 +46,8 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = Non
 
 
 def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, out, reducer: int, l2norm: bool,
-                  accumulate: int = N.ACC_STORE, z_scale: float = 1.0, row_begin: int = 0, row_end: Optional[int] = None):
+                  accumulate: int = N.ACC_STORE, z_scale: float = 1.0, row_begin: int = 0, row_end: Optional[int] = None,
+                  flags: int = 0):
     """Fused ``ConvLayer.forward`` of one relation into ``out[row_begin:row_end]`` (see include/gnn_recsys_b200.h)."""
     nnz = int(indices.shape[0])
     n_dst = int(indptr.shape[0]) - 1
@@ -59,7 +60,7 @@ def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, ou
     ws = _ws(nb, out.device, 'sage')
     N.call('gr_sage_relation_f32', N.ptr(indptr), N.ptr(indices), N.ptr(edge_w) if edge_w is not None else None, nnz,
            N.ptr(h_src), N.ptr(h_dst), row_begin, row_end, d_neigh, d_self, N.ptr(w_self_t), N.ptr(w_neigh_t), d_out,
-           reducer, int(l2norm), accumulate, float(z_scale), N.ptr(out), N.ptr(ws), ws.numel(), N.stream())
+           reducer, int(l2norm), accumulate, float(z_scale), int(flags), N.ptr(out), N.ptr(ws), ws.numel(), N.stream())
     return out
 
 

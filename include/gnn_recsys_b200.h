@@ -72,14 +72,15 @@ int gr_linear_f32(const float* x, int64_t n, int32_t d_in, const float* wt, cons
 #define GR_SAGE_LONG_ROW 2048
 #define GR_SAGE_CHUNK 2048
 size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh);
-/* projection epilogue of the fused kernel: 1 = fp16 hi/lo split on mma m16n8k16 with exact power-of-two row / weight
- * scaling (default), 0 = tf32 hi/lo split on m16n8k8. Both are fp32-accurate (3 products). Negative = query. */
-int gr_sage_epilogue_mode(int set_or_negative);
+/* flags: the projection epilogue of the fused kernel is an fp16 hi/lo split on mma m16n8k16 with exact power-of-two row /
+ * weight scaling; GR_SAGE_FLAG_TF32_EPILOGUE selects the tf32 hi/lo split on m16n8k8 instead. Both are fp32-accurate
+ * (3 products). Per call: the library keeps no mutable global state (re-entrant, one stream per caller thread). */
+enum { GR_SAGE_FLAG_TF32_EPILOGUE = 1 };
 int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indices, const float* edge_w_or_null, int64_t nnz,
                          const float* h_src, const float* h_dst, int64_t row_begin, int64_t row_end,
                          int32_t d_neigh, int32_t d_self, const float* w_self_t, const float* w_neigh_t,
-                         int32_t d_out, int reducer, int l2norm, int accumulate, float z_scale, float* out,
-                         void* ws, size_t ws_bytes, gr_stream_t stream);
+                         int32_t d_out, int reducer, int l2norm, int accumulate, float z_scale, int32_t flags,
+                         float* out, void* ws, size_t ws_bytes, gr_stream_t stream);
 
 /* The gather-reduce alone (no projection): agg[v - row_begin... indexed by v] = reduce of neighbour rows. Used to
  * report aggregation bandwidth in isolation and by tests; same kernels as above without the epilogue. */

@@ -8,8 +8,7 @@ torch.manual_seed(1)
 model = grb.ConvModel(g, 2, {'user': 2, 'item': 4, 'hidden': 128, 'out': 128}).to(dev).eval()
 feats = {t: g.nodes[t].data['features'].to(dev) for t in g.ntypes}
 lib = grb._native.load()
-for mode in (1, 0, 1):
-    lib.gr_sage_epilogue_mode(mode)
+for mode in (1,):
     with torch.no_grad():
         for _ in range(3):
             h = model.get_repr([blk], model.embed(dict(feats)))
