@@ -387,6 +387,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true')
     ap.add_argument('--one-layout', action='store_true', help='N>1: time only the primary scoring layout')
+    ap.add_argument('--equal-rows', action='store_true', help='N>1: cut the item id space by rows instead of by work')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS[args.config]
@@ -434,8 +435,10 @@ def main():
         ranges = {t: (0, n) for t, n in num.items()}
         blk = g.full_block_on(dev)
     else:  # SHARDED STORAGE: this rank ingests and keeps only the CSR rows / feature rows of its destination id ranges
-        ranges = D.node_ranges(num, world, rank)
-        blk = g.sharded_block_on(dev, ranges)
+        # (users: equal row ranges; items: ranges of equal WORK -- the most popular item alone holds ~8 % of the edges)
+        wb = {} if args.equal_rows else {'item': D.work_bounds(g, 'item', world)}
+        ranges = D.node_ranges(num, world, rank, wb)
+        blk = g.sharded_block_on(dev, ranges, bounds=wb)
     torch.cuda.synchronize()
     t_ingest = time.perf_counter() - t0
     blocks = [blk] * n_conv
@@ -464,7 +467,10 @@ def main():
             h = model.get_repr(blocks, h)
             mark('aggregate')
             return h
-        h = D.sharded_forward(model, blocks, feats, gather_last=('item',) if layout == 'user_shards' else ('user',), mark=mark)
+        # user_shards scores this rank's users against ALL items: only the item table is gathered after the last layer.
+        # item_shards needs all users and its own (equal-row) item range; the aggregation ranges of the items are cut
+        # by work, not rows, so the (small) item table is gathered too
+        h = D.sharded_forward(model, blocks, feats, gather_last=('item',) if layout == 'user_shards' else None, mark=mark)
         mark('aggregate')
         return h
 
@@ -555,8 +561,6 @@ def main():
             # 512 sampled users of the range this rank owns, against the brute-force fp32 kernel over ALL items
             ub, ue = own_range[layout]
             h_item_full = h['item']
-            if layout == 'item_shards':  # this layout never gathers the item table: do it here, for the checker only
-                h_item_full = D.allgather_rows(h['item'].clone(), n_items)
             sample = torch.from_numpy(ub + np.random.default_rng(rank).choice(ue - ub, min(512, ue - ub), replace=False)).to(dev)
             ex_tab = grb.ScoringTable(h_item_full, grb.RecsConfig(exact_only=True))
             ex_ids, ex_sc = grb.recommend_topk(h['user'][sample], ex_tab, K_RECS, bought.select(sample.cpu().numpy()))

@@ -21,6 +21,7 @@ ACC_STORE, ACC_ADD, ACC_MAX = 0, 1, 2
 ELEM_BF16, ELEM_FP16 = 0, 1
 SCORE_MAX_SPLITS = 32
 SCORE_FLAG_SINGLE_CTA = 1
+SCORE_FLAG_NO_TAIL_SPLIT = 2
 LINEAR_FLAG_LEGACY = 1
 SAGE_FLAG_TF32_EPILOGUE = 1
 

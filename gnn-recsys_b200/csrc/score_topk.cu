@@ -163,7 +163,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
                   long long n_users, long long n_items, long long item_id_base, int tiles_per_split, uint32_t idesc,
                   const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int kk,
                   const float* __restrict__ band_ptr, const int* __restrict__ user_map, int ring,
-                  float* __restrict__ sl_score, int* __restrict__ sl_id) {
+                  float* __restrict__ sl_score, int* __restrict__ sl_id, int full_pairs, int tail_c,
+                  float* __restrict__ tail_score, int* __restrict__ tail_id) {
   using L = Cfg<KB, PA, PAIR>;
   constexpr int D_PAD = KB * KBLK;
   constexpr int SLOT = L::SLOT_BYTES;
@@ -188,9 +189,21 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler as well
   const int lane = threadIdx.x & 31;
   const int n_tiles_all = (int)((n_items + TILE_N - 1) / TILE_N);
-  const int tile0 = blockIdx.y * tiles_per_split;
-  const int n_tiles = max(0, min(tiles_per_split, n_tiles_all - tile0));
-  const long long row_base = (long long)blockIdx.x * ROWS_PER_CTA;
+  // Work unit of this CTA (pair): normally users [blockIdx.x * 256, +256) x item split blockIdx.y. TAIL SPLIT (pairs,
+  // one split): the pairs of the last, partial wave -- index >= full_pairs -- are cut into tail_c item ranges each, so
+  // that the wave is tail_c times shorter instead of leaving most SM pairs idle for a whole sweep; their shortlists go
+  // to tail_score / tail_id ([range][tail row][S]) and are merged by the host side.
+  int split = blockIdx.y, per_split = tiles_per_split;
+  long long row_base = (long long)blockIdx.x * ROWS_PER_CTA;
+  const bool tail = PAIR && tail_c > 1 && (int)(blockIdx.x >> 1) >= full_pairs;
+  if (tail) {
+    const int qq = (int)(blockIdx.x >> 1) - full_pairs;
+    row_base = ((long long)(full_pairs + qq / tail_c) * 2 + (blockIdx.x & 1)) * ROWS_PER_CTA;
+    split = qq % tail_c;
+    per_split = (n_tiles_all + tail_c - 1) / tail_c;
+  }
+  const int tile0 = split * per_split;
+  const int n_tiles = max(0, min(per_split, n_tiles_all - tile0));
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, UT); }  // one commit per issuer
@@ -407,8 +420,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
     for (int L = 0; L < 32; ++L) {  // [split][row][S]: one coalesced row per iteration
       const long long r = row_base + t0 + L;
       if (r < n_users && lane < S) {
-        sl_score[((long long)blockIdx.y * n_users + r) * S + lane] = ls[(t0 + L) * lst + lane];
-        sl_id[((long long)blockIdx.y * n_users + r) * S + lane] = li[(t0 + L) * lst + lane];
+        if (tail) {
+          const long long tail_row0 = (long long)full_pairs * 2 * ROWS_PER_CTA;
+          const long long o = ((long long)split * (n_users - tail_row0) + (r - tail_row0)) * S + lane;
+          tail_score[o] = ls[(t0 + L) * lst + lane];
+          tail_id[o] = li[(t0 + L) * lst + lane];
+        } else {
+          sl_score[((long long)split * n_users + r) * S + lane] = ls[(t0 + L) * lst + lane];
+          sl_id[((long long)split * n_users + r) * S + lane] = li[(t0 + L) * lst + lane];
+        }
       }
     }
   }
@@ -441,7 +461,32 @@ struct ScoreArgs {
   const int* user_map;
   float* sl_score;
   int* sl_id;
+  int full_pairs, tail_c;   // tail split (see the kernel): 0 / 1 = off
+  float* tail_score;
+  int* tail_id;
 };
+
+// Tail split: with `pairs` CTA pairs on `slots` SM pairs the last wave holds pairs % slots of them. When that is at most
+// half the slots, each of its pairs is cut into c item ranges (all of them still resident at once).
+struct TailPlan { int full_pairs, tail_pairs, c; };
+TailPlan plan_tail(long long n_users, long long n_items) {
+  const long long pairs = ((n_users + ROWS_PER_CTA - 1) / ROWS_PER_CTA + 1) / 2;
+  const int slots = gr::sm_count() / 2;
+  const long long tiles = (n_items + TILE_N - 1) / TILE_N;
+  TailPlan p{0, 0, 1};
+  if (slots <= 0 || pairs <= slots) return p;
+  const int tail = (int)(pairs % slots);
+  if (tail == 0 || 2 * tail > slots) return p;
+  const int c = (int)std::min<long long>(std::min<long long>(slots / tail, 8), tiles / 64);  // >= 64 tiles per range
+  if (c < 2) return p;
+  p.full_pairs = (int)(pairs - tail); p.tail_pairs = tail; p.c = c;
+  return p;
+}
+size_t tail_half_bytes(const TailPlan& p, long long n_users, int S) {
+  if (p.c < 2) return 0;
+  const long long tail_rows = n_users - (long long)p.full_pairs * 2 * ROWS_PER_CTA;
+  return gr::align_up((size_t)p.c * tail_rows * S * 4, 256);
+}
 
 template <int KB, int PA, int PB, bool PAIR>
 int launch_score(const ScoreArgs& a, cudaStream_t st) {
@@ -465,12 +510,15 @@ int launch_score(const ScoreArgs& a, cudaStream_t st) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (a.tail_c > 1) cfg.gridDim = dim3(2u * (unsigned)(a.full_pairs + (gx / 2 - a.full_pairs) * a.tail_c), 1u);
     GR_CUDA(cudaLaunchKernelEx(&cfg, kern, a.mu, a.mi_half, a.n_users, a.n_items, a.item_id_base, a.tiles_per_split,
-                               idesc, a.bptr, a.bids, a.S, a.k, a.band, a.user_map, ring, a.sl_score, a.sl_id));
+                               idesc, a.bptr, a.bids, a.S, a.k, a.band, a.user_map, ring, a.sl_score, a.sl_id,
+                               a.full_pairs, a.tail_c, a.tail_score, a.tail_id));
   } else {
     kern<<<dim3(gx, (unsigned)a.splits), NUM_THREADS, smem, st>>>(a.mu, a.mi, a.n_users, a.n_items, a.item_id_base,
                                                                   a.tiles_per_split, idesc, a.bptr, a.bids, a.S, a.k,
-                                                                  a.band, a.user_map, ring, a.sl_score, a.sl_id);
+                                                                  a.band, a.user_map, ring, a.sl_score, a.sl_id, 0, 1,
+                                                                  nullptr, nullptr);
   }
   GR_LAUNCH_CHECK();
   return GR_OK;
@@ -507,7 +555,7 @@ extern "C" int gr_score_splits(int64_t n_users, int64_t n_items) {
 extern "C" size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t shortlist) {
   if (n_users <= 0 || n_items <= 0) return 256;
   const int splits = choose_splits(n_users, n_items);
-  if (splits == 1) return 256;
+  if (splits == 1) return std::max<size_t>(256, 2 * tail_half_bytes(plan_tail(n_users, n_items), n_users, shortlist));
   return gr::align_up((size_t)splits * n_users * shortlist * 4, 256) * 2;
 }
 
@@ -567,6 +615,20 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
     part_id = reinterpret_cast<int*>(static_cast<char*>(ws) + half);
   }
   a.sl_score = part_score; a.sl_id = part_id;
+  a.full_pairs = 0; a.tail_c = 1; a.tail_score = nullptr; a.tail_id = nullptr;
+  TailPlan tp{0, 0, 1};
+  const bool pair_kernel = d_pad >= 128 && !(d_pad == 128 && (flags & GR_SCORE_FLAG_SINGLE_CTA));
+  if (a.splits == 1 && pair_kernel && !(flags & GR_SCORE_FLAG_NO_TAIL_SPLIT)) {
+    tp = plan_tail(n_users, n_items);
+    const size_t half = tail_half_bytes(tp, n_users, shortlist);
+    if (tp.c > 1 && ws != nullptr && ws_bytes >= 2 * half) {
+      a.full_pairs = tp.full_pairs; a.tail_c = tp.c;
+      a.tail_score = static_cast<float*>(ws);
+      a.tail_id = reinterpret_cast<int*>(static_cast<char*>(ws) + half);
+    } else {
+      tp.c = 1;
+    }
+  }
   if (d_pad == 64) rc = launch_scheme<1, false>(a, parts_users, parts_items, st);
   else if (d_pad == 192) rc = launch_score<3, 1, 1, true>(a, st);
   else if (d_pad == 256) rc = launch_score<4, 1, 1, true>(a, st);
@@ -575,5 +637,10 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   if (rc != GR_OK) return rc;
   if (a.splits > 1)
     return gr_topk_merge(part_score, part_id, a.splits, n_users, shortlist, shortlist, sl_score, sl_id, stream);
+  if (a.tail_c > 1) {  // merge the item ranges of the tail pairs' rows into the final lists
+    const long long tail_row0 = (long long)a.full_pairs * 2 * ROWS_PER_CTA;
+    return gr_topk_merge(a.tail_score, a.tail_id, a.tail_c, n_users - tail_row0, shortlist, shortlist,
+                         sl_score + tail_row0 * shortlist, sl_id + tail_row0 * shortlist, stream);
+  }
   return GR_OK;
 }

@@ -379,12 +379,15 @@ class HeteroGraph:
             self._dev_blocks[key] = Block(rels, self._num, self._num)
         return self._dev_blocks[key]
 
-    def sharded_block_on(self, device, ranges: Dict[str, Tuple[int, int]], edge_weight: Optional[str] = None) -> Block:
+    def sharded_block_on(self, device, ranges: Dict[str, Tuple[int, int]], edge_weight: Optional[str] = None,
+                         bounds=None) -> Block:
         """This rank's SHARD of the full-graph block (multi-GPU, ``distributed.py``): for every relation only the CSR
         rows of the destination range ``ranges[dst ntype] = (begin, end)`` -- ``indptr`` has ``end - begin + 1``
         entries and starts at 0, ``indices`` are GLOBAL source ids, ``eperm`` holds the global edge id of each slot.
         Only this rank's edges travel to the device, so the resident graph is ~1/world of the full CSR
-        (``Block.shard_ranges`` marks the block; ``HeteroGraphConv`` then computes exactly those rows)."""
+        (``Block.shard_ranges`` marks the block; ``HeteroGraphConv`` then computes exactly those rows). ``bounds``:
+        ``{ntype: world + 1 boundaries}`` of the node types whose ranges are NOT the equal-row ``shard_range`` cut
+        (``distributed.work_bounds``), recorded so that ``sharded_forward`` all-gathers them as unequal chunks."""
         key = (str(device), edge_weight, tuple(sorted(ranges.items())))
         if key not in self._dev_blocks:
             from . import ops
@@ -404,6 +407,7 @@ class HeteroGraph:
                 rels[c] = Relation(indptr, indices, self._num[c[0]], e - b, eid.to(torch.int32), w)
             blk = Block(rels, self._num, self._num)
             blk.shard_ranges = {t: (int(b), int(e)) for t, (b, e) in ranges.items()}
+            blk.shard_bounds = {t: [int(x) for x in v] for t, v in (bounds or {}).items()}  # types cut by work (unequal)
             self._dev_blocks[key] = blk
         return self._dev_blocks[key]
 
@@ -493,12 +497,15 @@ class DeviceEdgeGraph:
     def edges(self):
         return _TypedIndex(self._edge_frames, self.to_canonical_etype)
 
-    def sharded_block_on(self, device, ranges: Dict[str, Tuple[int, int]], edge_weight: Optional[str] = None) -> Block:
+    def sharded_block_on(self, device, ranges: Dict[str, Tuple[int, int]], edge_weight: Optional[str] = None,
+                         bounds=None) -> Block:
         """This rank's SHARD of the full-graph block (multi-GPU, ``distributed.py``): for every relation only the CSR
         rows of the destination range ``ranges[dst ntype] = (begin, end)`` -- ``indptr`` has ``end - begin + 1``
         entries and starts at 0, ``indices`` are GLOBAL source ids, ``eperm`` holds the global edge id of each slot.
         Only this rank's edges travel to the device, so the resident graph is ~1/world of the full CSR
-        (``Block.shard_ranges`` marks the block; ``HeteroGraphConv`` then computes exactly those rows)."""
+        (``Block.shard_ranges`` marks the block; ``HeteroGraphConv`` then computes exactly those rows). ``bounds``:
+        ``{ntype: world + 1 boundaries}`` of the node types whose ranges are NOT the equal-row ``shard_range`` cut
+        (``distributed.work_bounds``), recorded so that ``sharded_forward`` all-gathers them as unequal chunks."""
         key = (str(device), edge_weight, tuple(sorted(ranges.items())))
         if key not in self._dev_blocks:
             from . import ops
@@ -518,6 +525,7 @@ class DeviceEdgeGraph:
                 rels[c] = Relation(indptr, indices, self._num[c[0]], e - b, eid.to(torch.int32), w)
             blk = Block(rels, self._num, self._num)
             blk.shard_ranges = {t: (int(b), int(e)) for t, (b, e) in ranges.items()}
+            blk.shard_bounds = {t: [int(x) for x in v] for t, v in (bounds or {}).items()}  # types cut by work (unequal)
             self._dev_blocks[key] = blk
         return self._dev_blocks[key]
 

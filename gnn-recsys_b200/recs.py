@@ -42,6 +42,11 @@ class RecsConfig:
     acc_err: float = 1.5e-6       # allowance for fp32 accumulation error of the tensor-core sum, relative to |x||y|
     exact_only: bool = False      # skip the tensor-core path (brute-force fp32 kernel for every user)
     single_cta: bool = False      # cta_group::1 kernel instead of CTA pairs (same results; tests / experiments)
+    tail_split: bool = True       # cut the user tiles of the last, partial wave into item ranges (wave quantisation)
+    small_items: int = 32768      # calls with fewer items than this AND fewer than small_work scores take the 3-product
+    small_work: int = 1 << 31     # scheme directly with its 16-entry shortlist: a sweep that short is all shortlist
+    #                               warm-up, and the single product's proof would only add a second pass (and a host
+    #                               read) to a launch-bound step (c1: 10k x 5k)
     parts: Optional[int] = None   # shorthand: parts=1 -> (1, 1), parts=2 -> (2, 2) and no second pass
 
     def __post_init__(self):
@@ -65,7 +70,7 @@ class RecsConfig:
 
     @property
     def flags(self) -> int:
-        return N.SCORE_FLAG_SINGLE_CTA if self.single_cta else 0
+        return (N.SCORE_FLAG_SINGLE_CTA if self.single_cta else 0) | (0 if self.tail_split else N.SCORE_FLAG_NO_TAIL_SPLIT)
 
 
 def elem_type_of(elem: str) -> int:
@@ -163,7 +168,7 @@ class ScoringTable:
         self.cfg, self.item_id_base = cfg, int(item_id_base)
         self.n_items, self.d = h_item.shape
         self.tc = (not cfg.exact_only) and self.d <= 256 and self.n_items > 0
-        self.center, self.items_q, self.stats = None, None, None
+        self.center = None
         self._ops = {}
         if self.tc:
             self.d_pad = 64 * ((self.d + 63) // 64)
@@ -172,7 +177,14 @@ class ScoringTable:
                 self.cfg = cfg = replace(cfg, parts=None, parts_users=1, parts_items=1, second=None)
             if cfg.center:
                 self.center = ops.colmean_normalized(self.h_item)
-            self.items_q, self.stats = self.operands(cfg.elem, cfg.parts_items)
+
+    @property
+    def items_q(self):  # operand rows / residual statistics of the configuration's own (first-pass) scheme
+        return self.operands(self.cfg.elem, self.cfg.parts_items)[0] if self.tc else None
+
+    @property
+    def stats(self):
+        return self.operands(self.cfg.elem, self.cfg.parts_items)[1] if self.tc else None
 
     def operands(self, elem: str, parts: int):
         key = (elem, parts)
@@ -224,24 +236,33 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
         return (ids, scores, (0, 0)) if return_overflow else (ids, scores)
     if cfg.shortlist > 32:
         raise ValueError('shortlist above 32 is not supported by the fused top-k epilogue')
-    first = (cfg.elem, cfg.parts_users, cfg.parts_items, cfg.shortlist)
+    first, second = (cfg.elem, cfg.parts_users, cfg.parts_items, cfg.shortlist), cfg.second
+    if second is not None and cfg.products < 3 and table.n_items < cfg.small_items and n * table.n_items < cfg.small_work:
+        first, second = second, None   # short sweep: the fp32-grade scheme directly (see RecsConfig.small_items)
     ids, scores, overflow, n_overflow = _tc_pass(h_user, table, k, bptr, bids, first, cfg, mark=mark)
     mark('rescore_end')
     n1 = n2 = 0
-    if n > 0:
-        n1 = int(n_overflow.item())  # the one host read of the pipeline: sizes pass 2 (usually < 1 % of the users)
-    if n1 > 0 and cfg.second is not None:
-        # pass 2: the users pass 1 could not prove, compacted, through the more accurate scheme
-        rows = overflow[:n1].sort().values  # ascending: deterministic whatever order the proof kernel appended in
-        ids2, scores2, overflow, n_overflow = _tc_pass(h_user[rows.long()], table, k, bptr, bids, cfg.second, cfg,
-                                                       user_map=rows)
-        ids[rows.long()] = ids2
-        scores[rows.long()] = scores2
-        n2 = int(n_overflow.item())
+    if second is None:
+        # no tensor-core second pass: the exact kernel reads the overflow count on the device (no host read at all)
+        if n > 0:
+            ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS, user_list=overflow,
+                                 n_list=n_overflow, out_ids=ids, out_scores=scores)
+            if return_overflow:
+                n1 = n2 = int(n_overflow.item())
     else:
-        n2 = n1
-    if n2 > 0:  # exact fp32 pass for whoever is left (device-side list)
-        ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS, user_list=overflow,
-                             n_list=n_overflow, out_ids=ids, out_scores=scores)
+        if n > 0:
+            n1 = int(n_overflow.item())  # the one host read of the pipeline: sizes pass 2 (usually < 1 % of the users)
+        if n1 > 0:
+            # pass 2: the users pass 1 could not prove, compacted, through the more accurate scheme
+            rows = overflow[:n1].sort().values  # ascending: deterministic whatever order the proof kernel appended in
+            ids2, scores2, overflow, n_overflow = _tc_pass(h_user[rows.long()], table, k, bptr, bids, second, cfg,
+                                                           user_map=rows)
+            ids[rows.long()] = ids2
+            scores[rows.long()] = scores2
+            # exact fp32 pass for whoever is left (device-side list and count)
+            ops.score_topk_exact(h_user, table.h_item, table.item_id_base, bptr, bids, k, COS_EPS, user_list=overflow,
+                                 n_list=n_overflow, out_ids=ids, out_scores=scores)
+            if return_overflow:
+                n2 = int(n_overflow.item())
     mark('fallback_end')
     return (ids, scores, (n1, n2)) if return_overflow else (ids, scores)

@@ -114,7 +114,8 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *           (band: device float, NULL = +inf = plain S-th-best rule). user_map (optional int32[n_users]): row u's
  *           bought list is that of user user_map[u] (second pass over a compacted user subset). Output: per user `shortlist` approximate
  *           (centred) scores, descending, and their global item ids (-1 = empty slot).
- *           flags: GR_SCORE_FLAG_SINGLE_CTA = cta_group::1 kernel instead of CTA pairs (same results).
+ *           flags: GR_SCORE_FLAG_SINGLE_CTA = cta_group::1 kernel instead of CTA pairs (same results);
+ *           GR_SCORE_FLAG_NO_TAIL_SPLIT = do not cut the user tiles of the last, partial wave into item ranges.
  *  stage 2  gr_rescore_topk_f32: exact fp32 cosine (torch formula x.y / sqrt(max(|x|^2 |y|^2, eps^2))) of the
  *           shortlisted items that can still reach the top-k, sorted by (score desc, id asc), first k. Proves per user
  *           that no item outside the shortlist can enter the top-k by more than tie_tol. With the user's own rounding
@@ -133,7 +134,7 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *  merge    gr_topk_merge: row-wise merge of `parts` partial (score desc, id) lists into the k_out best
  *           (scores[p][u][k_in]); ties by smaller id; ids < 0 are empty slots. */
 enum { GR_ELEM_BF16 = 0, GR_ELEM_FP16 = 1 };
-enum { GR_SCORE_FLAG_SINGLE_CTA = 1 };
+enum { GR_SCORE_FLAG_SINGLE_CTA = 1, GR_SCORE_FLAG_NO_TAIL_SPLIT = 2 };
 #define GR_SCORE_MAX_SPLITS 32
 size_t gr_colmean_workspace_bytes(int64_t n, int32_t d);
 int gr_colmean_normalized_f32(const float* x, int64_t n, int32_t d, float* center, void* ws, size_t ws_bytes,

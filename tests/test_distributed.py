@@ -131,6 +131,15 @@ def _worker_sharded(rank, world, port, ret):
                 got = D.sharded_forward(model, [sblk] * (n_layers - 1), local)
                 for t in want:
                     assert torch.allclose(got[t], want[t], rtol=1e-6, atol=1e-7), (t, agg)
+                # items cut by WORK (unequal ranges), users by rows
+                wb = {'item': D.work_bounds(g, 'item', world)}
+                assert wb['item'][0] == 0 and wb['item'][-1] == 77
+                r2 = D.node_ranges(num, world, rank, wb)
+                sb2 = g.sharded_block_on('cpu', r2, bounds=wb)
+                loc2 = {t: feats[t][r2[t][0]:r2[t][1]] for t in feats}
+                got2 = D.sharded_forward(model, [sb2] * (n_layers - 1), loc2)
+                for t in want:
+                    assert torch.allclose(got2[t], want[t], rtol=1e-6, atol=1e-7), (t, agg, 'work bounds')
                 part = D.sharded_forward(model, [sblk] * (n_layers - 1), local, gather_last=('item',))
                 ub, ue = ranges['user']
                 assert torch.allclose(part['user'][ub:ue], want['user'][ub:ue], rtol=1e-6, atol=1e-7)

@@ -76,8 +76,9 @@ def test_embeddings_minibatch_loader(grb, name):
         np.testing.assert_allclose(y[t].numpy(), z['emb/' + t], rtol=RTOL, atol=ATOL)
 
 
-RECS_CONFIGS = [dict(), dict(parts_users=2, parts_items=1), dict(k_band=False, shortlist=16), dict(single_cta=True),
-                dict(second=None), dict(elem='bf16', second=('bf16', 2, 2, 16)),
+T = dict(small_items=0)  # the fixtures' item tables are tiny: keep them on the tiered path they are meant to exercise
+RECS_CONFIGS = [dict(), dict(T), dict(T, parts_users=2, parts_items=1), dict(T, k_band=False, shortlist=16),
+                dict(T, single_cta=True), dict(T, second=None), dict(T, elem='bf16', second=('bf16', 2, 2, 16)),
                 dict(elem='bf16', parts=2), dict(elem='fp16', parts=2), dict(elem='bf16', parts=1),
                 dict(elem='fp16', parts=1, center=False), dict(exact_only=True), dict(elem='bf16', parts=2, tie_tol=0.0)]
 
@@ -502,7 +503,7 @@ def test_quantised_scores_within_error_bound(grb, cfg):
     rng = np.random.default_rng(11)
     d, n_u, n_i = 128, 512, 4096
     hu, hi = clustered_embeddings(rng, n_u, d, 0.3).cuda(), clustered_embeddings(rng, n_i, d, 0.3).cuda()
-    c = grb.RecsConfig(shortlist=32, k_band=False, **cfg)
+    c = grb.RecsConfig(shortlist=32, k_band=False, small_items=0, **cfg)
     table = grb.ScoringTable(hi, c)
     users_q, ustats = grb.ops.score_prep(hu, None, table.d_pad, c.parts_users, c.elem_type, True)
     sl_s, sl_i = grb.ops.score_topk_tc(users_q, table.items_q, 0, table.d_pad, c.parts_users, c.parts_items, c.elem_type,
@@ -536,7 +537,7 @@ def test_k_band_threshold_keeps_every_possible_top_k_item(grb):
     rng = np.random.default_rng(3)
     d, n_u, n_i, k = 128, 300, 6000, 10
     hu, hi = clustered_embeddings(rng, n_u, d, 0.3).cuda(), clustered_embeddings(rng, n_i, d, 0.3).cuda()
-    c = grb.RecsConfig()
+    c = grb.RecsConfig(small_items=0)
     table = grb.ScoringTable(hi, c)
     users_q, ustats = grb.ops.score_prep(hu, None, table.d_pad, 1, c.elem_type, True)
     band = grb.ops.score_band(table.stats, ustats, c.elem_type, 1, 1, c.acc_err)
@@ -557,11 +558,13 @@ def test_k_band_threshold_keeps_every_possible_top_k_item(grb):
 def test_recs_large_vs_exact_kernel_and_oracle(grb, shape, pair):
     """Tensor-core path (both kernel variants, tiered passes) == brute-force fp32 kernel == oracle (vectorised) on
     clustered embeddings with bought lists."""
-    _recs_large(grb, shape, grb.RecsConfig(single_cta=not pair))
+    _recs_large(grb, shape, grb.RecsConfig(single_cta=not pair, small_items=0))
+    if pair:
+        _recs_large(grb, shape, grb.RecsConfig())   # small tables: routed straight to the 3-product scheme
 
 
 @pytest.mark.parametrize('cfg', [dict(shortlist=12), dict(shortlist=16, second=('fp16', 2, 1, 32)), dict(second=None, shortlist=10),
-                                 dict(elem='bf16', second=('bf16', 2, 2, 16))],
+                                 dict(elem='bf16', shortlist=16, second=('bf16', 2, 2, 16))],
                          ids=['S12', 'second-2product', 'S10-nosecond', 'bf16-tiers'])
 def test_recs_tiers_are_exercised(grb, cfg):
     """Clusters of 30 near-duplicate items (1e-4 apart: inside the single-product error, far outside the 3-product
@@ -571,10 +574,41 @@ def test_recs_tiers_are_exercised(grb, cfg):
     hi = base.repeat_interleave(30, dim=0) + 1e-4 * torch.from_numpy(rng.standard_normal((9000, 128)).astype(np.float32))
     hi = torch.nn.functional.normalize(hi[torch.from_numpy(rng.permutation(9000))], dim=1).contiguous()
     hu = clustered_embeddings(rng, 3000, 128, 0.2)
-    n1, n2 = _recs_large(grb, (3000, 9000), grb.RecsConfig(**cfg), tables=(hu, hi))
+    n1, n2 = _recs_large(grb, (3000, 9000), grb.RecsConfig(small_items=0, **cfg), tables=(hu, hi))
     assert n1 > 1000
     if cfg.get('second', True) is not None and cfg.get('elem', 'fp16') == 'fp16':
         assert n2 < n1 // 10      # the fp16 second passes (err ~1e-6 / ~1e-4) prove (nearly) everyone the first could not
+
+
+def test_tail_wave_split_gives_the_same_shortlists(grb):
+    """Wave quantisation: with more CTA pairs than SM pairs, the pairs of the last partial wave are cut into item ranges
+    (merged afterwards). 45 000 users = 88 pairs on 74 SM pairs -> 14 tail pairs x 2 ranges; the shortlists must equal
+    the unsplit kernel's entry for entry, on both sides of the tail boundary, with bought lists."""
+    rng = np.random.default_rng(45)
+    n_u, n_i, d = 45000, 20000, 128
+    hu, hi = clustered_embeddings(rng, n_u, d, 0.2).cuda(), clustered_embeddings(rng, n_i, d, 0.2).cuda()
+    bu = np.repeat(np.arange(n_u), 2)
+    bought = grb.BoughtCSR.from_edges(bu, rng.integers(0, n_i, bu.size), n_u)
+    bptr, bids = bought.on(hu.device)
+    c = grb.RecsConfig(small_items=0)
+    table = grb.ScoringTable(hi, c)
+    uq, ust = grb.ops.score_prep(hu, None, 128, 1, c.elem_type, True)
+    band = grb.ops.score_band(table.stats, ust, c.elem_type, 1, 1, c.acc_err)
+    N = grb._native
+    a_s, a_i = grb.ops.score_topk_tc(uq, table.items_q, 0, 128, 1, 1, c.elem_type, bptr, bids, 32, 10, band)
+    b_s, b_i = grb.ops.score_topk_tc(uq, table.items_q, 0, 128, 1, 1, c.elem_type, bptr, bids, 32, 10, band,
+                                     flags=N.SCORE_FLAG_NO_TAIL_SPLIT)
+    # the k-band rule may keep different STALE entries below tau_k - band (they depend on arrival order); everything
+    # that can matter -- entries at or above the final threshold -- must agree exactly
+    tau = torch.maximum(b_s[:, 31], b_s[:, 9] - float(band))[:, None]
+    for s1, i1, s2, i2 in ((a_s, a_i, b_s, b_i), (b_s, b_i, a_s, a_i)):
+        keep = s1 > tau
+        hit = (i1[:, :, None] == i2[:, None, :]).any(-1)
+        assert bool((hit | ~keep).all())
+    assert torch.equal(a_s[:, :10], b_s[:, :10]) and torch.equal(a_i[:, :10], b_i[:, :10])
+    ids, sc, n_over = grb.recommend_topk(hu, table, 10, bought, return_overflow=True)
+    ex_ids, ex_sc = grb.recommend_topk(hu, grb.ScoringTable(hi, grb.RecsConfig(exact_only=True)), 10, bought)
+    assert float((sc - ex_sc).abs().max()) < 1e-5
 
 
 def _recs_large(grb, shape, cfg, tables=None):
@@ -655,7 +689,7 @@ def test_duplicate_items_overflow_path_and_fp16_never_overflows(grb):
         if elem == 'fp16':
             assert n_over == (0, 0)
     # the default tiers: the single fp16 product cannot prove a 100-fold tie, the fp16 3-product pass can
-    ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), grb.RecsConfig()), 10, None, return_overflow=True)
+    ids, sc, n_over = grb.recommend_topk(hu.to(dev), grb.ScoringTable(hi.to(dev), grb.RecsConfig(small_items=0)), 10, None, return_overflow=True)
     assert_topk_equivalent(ids.cpu().numpy().astype(np.int64), want, scores, 10)
     assert n_over[0] > 0 and n_over[1] == 0
 

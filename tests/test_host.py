@@ -191,7 +191,7 @@ def test_error_bound_arithmetic():
             if (pu, pi) == (2, 2):
                 assert bound < (2e-5 if elem == 'bf16' else 1e-6)
     c = grb.RecsConfig()
-    assert (c.elem, c.products, c.shortlist) == ('fp16', 1, 32) and c.second == ('fp16', 2, 2, 16)
+    assert (c.elem, c.products, c.shortlist, c.small_items) == ('fp16', 1, 32, 32768) and c.second == ('fp16', 2, 2, 16)
     assert grb.RecsConfig(parts=2, elem='bf16').products == 3 and grb.RecsConfig(parts=2).second is None
     with pytest.raises(ValueError):
         grb.RecsConfig(parts_users=1, parts_items=2)
