@@ -36,8 +36,10 @@ SIGNATURES = {
     'gr_linear_workspace_bytes': (_sz, [_i64, _i32, _i32]),
     'gr_linear_f32': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, C.c_int, _i32, _vp, _vp, _sz, _vp]),
     'gr_sage_relation_workspace_bytes': (_sz, [_i64, _i32]),
+    'gr_sage_packed_weights_bytes': (_sz, [_i32, _i32, _i32]),
+    'gr_sage_pack_weights': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'gr_sage_relation_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _i32, C.c_int,
-                                       C.c_int, C.c_int, _f32, _i32, _vp, _vp, _sz, _vp]),
+                                       C.c_int, C.c_int, _f32, _i32, _vp, _vp, _vp, _sz, _vp]),
     'gr_gather_reduce_f32': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, C.c_int, _vp, _vp, _sz, _vp]),
     'gr_edge_cosine_f32': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     'gr_colmean_workspace_bytes': (_sz, [_i64, _i32]),

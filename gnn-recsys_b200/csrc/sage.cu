@@ -880,7 +880,44 @@ bool fast_dims(int dn, int ds, int dout) {
 
 size_t packed_bytes(int dn, int ds, int dout) { return gr::align_up((size_t)(dn + ds) * dout * 2 * sizeof(float), 256) + 256; }
 
+// [256 bytes: wscale {2^p, 2^-p}][packed B fragments]: what the fused kernel reads instead of the fp32 weights
+int pack_weights(const float* w_self_t, const float* w_neigh_t, int d_self, int d_neigh, int d_out, bool f16, char* dst,
+                 cudaStream_t st) {
+  float* wscale = reinterpret_cast<float*>(dst);
+  float4* packed = reinterpret_cast<float4*>(dst + 256);
+  if (f16) {
+    weight_scale_kernel<<<1, 1024, 0, st>>>(w_self_t, w_neigh_t, d_self * d_out, d_neigh * d_out, wscale);
+    GR_LAUNCH_CHECK();
+    const int total = (d_neigh + d_self) / 16 * (d_out / 8) * 32;
+    pack_weights_f16_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, wscale,
+                                                                 reinterpret_cast<uint4*>(packed));
+    GR_LAUNCH_CHECK();
+  } else {
+    const int total = (d_neigh + d_self) / 8 * (d_out / 8) * 32;
+    pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, packed);
+    GR_LAUNCH_CHECK();
+  }
+  return GR_OK;
+}
+
+bool use_f16(int32_t flags, int d_neigh, int d_self) {
+  return !(flags & GR_SAGE_FLAG_TF32_EPILOGUE) && d_neigh % 16 == 0 && d_self % 16 == 0;
+}
+
 }  // namespace
+
+extern "C" size_t gr_sage_packed_weights_bytes(int32_t d_neigh, int32_t d_self, int32_t d_out) {
+  return fast_dims(d_neigh, d_self, d_out) ? packed_bytes(d_neigh, d_self, d_out) : 0;
+}
+
+extern "C" int gr_sage_pack_weights(const float* w_self_t, const float* w_neigh_t, int32_t d_neigh, int32_t d_self,
+                                    int32_t d_out, int32_t flags, void* packed, gr_stream_t stream) {
+  GR_REQUIRE(fast_dims(d_neigh, d_self, d_out), GR_E_INVALID, "these dimensions do not use packed weights");
+  GR_REQUIRE(w_self_t && w_neigh_t && packed, GR_E_INVALID, "null pointer");
+  GR_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, GR_E_INVALID, "packed buffer must be 256-byte aligned");
+  return pack_weights(w_self_t, w_neigh_t, d_self, d_neigh, d_out, use_f16(flags, d_neigh, d_self),
+                      static_cast<char*>(packed), static_cast<cudaStream_t>(stream));
+}
 
 extern "C" size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh) {
   return long_ws_layout(nnz < 0 ? 0 : nnz, d_neigh, nullptr, nullptr) + packed_bytes(256, 256, 256);
@@ -890,8 +927,8 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
                                     int64_t nnz, const float* h_src, const float* h_dst, int64_t row_begin,
                                     int64_t row_end, int32_t d_neigh, int32_t d_self, const float* w_self_t,
                                     const float* w_neigh_t, int32_t d_out, int reducer, int l2norm, int accumulate,
-                                    float z_scale, int32_t flags, float* out, void* ws, size_t ws_bytes,
-                                    gr_stream_t stream) {
+                                    float z_scale, int32_t flags, const void* packed_or_null, float* out, void* ws,
+                                    size_t ws_bytes, gr_stream_t stream) {
   GR_REQUIRE(row_begin >= 0 && row_end >= row_begin, GR_E_INVALID, "bad row range");
   GR_REQUIRE(d_neigh > 0 && d_self > 0 && d_out > 0 && d_neigh <= 512 && d_self <= 512 && d_out <= 512, GR_E_INVALID,
              "dimensions must be in [1, 512]");
@@ -911,21 +948,16 @@ extern "C" int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indice
     GR_REQUIRE(ws != nullptr && ws_bytes >= need, GR_E_WORKSPACE, "workspace too small");
     GR_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, GR_E_INVALID, "workspace must be 256-byte aligned");
     long_ws_layout(nnz, d_neigh, &lw, static_cast<char*>(ws));
-    float* wscale = reinterpret_cast<float*>(static_cast<char*>(ws) + long_bytes);
-    float4* packed = reinterpret_cast<float4*>(static_cast<char*>(ws) + long_bytes + 256);
-    const bool f16 = !(flags & GR_SAGE_FLAG_TF32_EPILOGUE) && d_neigh % 16 == 0 && d_self % 16 == 0;
-    if (f16) {
-      weight_scale_kernel<<<1, 1024, 0, st>>>(w_self_t, w_neigh_t, d_self * d_out, d_neigh * d_out, wscale);
-      GR_LAUNCH_CHECK();
-      const int total = (d_neigh + d_self) / 16 * (d_out / 8) * 32;
-      pack_weights_f16_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, wscale,
-                                                                   reinterpret_cast<uint4*>(packed));
-      GR_LAUNCH_CHECK();
-    } else {
-      const int total = (d_neigh + d_self) / 8 * (d_out / 8) * 32;
-      pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_self_t, w_neigh_t, d_self, d_neigh, d_out, packed);
-      GR_LAUNCH_CHECK();
+    const bool f16 = use_f16(flags, d_neigh, d_self);
+    const char* pk = static_cast<const char*>(packed_or_null);
+    if (pk == nullptr) {  // not packed by the caller (gr_sage_pack_weights, once per weight update): pack per call
+      char* own = static_cast<char*>(ws) + long_bytes;
+      const int rcp = pack_weights(w_self_t, w_neigh_t, d_self, d_neigh, d_out, f16, own, st);
+      if (rcp != GR_OK) return rcp;
+      pk = own;
     }
+    const float* wscale = reinterpret_cast<const float*>(pk);
+    const float4* packed = reinterpret_cast<const float4*>(pk + 256);
     p.packed = packed;
     p.wscale = wscale;
     p.tile_counter = lw.counters + 2;  // zeroed by launch_long_rows below (it clears all 256 bytes of counters)

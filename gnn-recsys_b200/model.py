@@ -82,7 +82,17 @@ class ConvLayer(nn.Module):
         if aggregator_type in _LSTM:
             raise NotImplementedError('lstm aggregators are outside the accelerated hot path (DESIGN.md, scope)')
         self._wt_self, self._wt_neigh, self._wt_pre = _TransposedWeight(), _TransposedWeight(), _TransposedWeight()
+        self._packed_key, self._packed = None, None
         self.reset_parameters()
+
+    def _packed_weights(self, wst: torch.Tensor, wnt: torch.Tensor):
+        """Split / packed form of (fc_self, fc_neigh) for the fused kernel, rebuilt only when a weight changed."""
+        ws, wn = self.fc_self.weight, self.fc_neigh.weight
+        key = (ws.data_ptr(), ws._version, wn.data_ptr(), wn._version, str(ws.device))
+        if key != self._packed_key:
+            self._packed = ops.sage_pack_weights(wst, wnt)
+            self._packed_key = key
+        return self._packed
 
     def forward(self, graph, x, cetype=None, out=None, accumulate=N.ACC_STORE, z_scale=1.0, row_begin=0,
                 row_end=None):
@@ -104,9 +114,10 @@ class ConvLayer(nn.Module):
         reducer = N.REDUCE_MAX if base == 'pool_nn' else N.REDUCE_MEAN
         if out is None:
             out = torch.empty((h_self.shape[0], self._out_feats), dtype=torch.float32, device=h_self.device)
-        return ops.sage_relation(graph.indptr, graph.indices, edge_w, h_neigh, h_self.contiguous(),
-                                 self._wt_self.get(self.fc_self.weight), self._wt_neigh.get(self.fc_neigh.weight), out,
-                                 reducer, bool(self.norm), accumulate, z_scale, row_begin, row_end)
+        wst, wnt = self._wt_self.get(self.fc_self.weight), self._wt_neigh.get(self.fc_neigh.weight)
+        return ops.sage_relation(graph.indptr, graph.indices, edge_w, h_neigh, h_self.contiguous(), wst, wnt, out,
+                                 reducer, bool(self.norm), accumulate, z_scale, row_begin, row_end,
+                                 packed=self._packed_weights(wst, wnt))
 
 
 class HeteroGraphConv(nn.Module):

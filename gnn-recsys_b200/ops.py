@@ -47,7 +47,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = Non
 
 def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, out, reducer: int, l2norm: bool,
                   accumulate: int = N.ACC_STORE, z_scale: float = 1.0, row_begin: int = 0, row_end: Optional[int] = None,
-                  flags: int = 0):
+                  flags: int = 0, packed: Optional[torch.Tensor] = None):
     """Fused ``ConvLayer.forward`` of one relation into ``out[row_begin:row_end]`` (see include/gnn_recsys_b200.h)."""
     nnz = int(indices.shape[0])
     n_dst = int(indptr.shape[0]) - 1
@@ -60,8 +60,23 @@ def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, ou
     ws = _ws(nb, out.device, 'sage')
     N.call('gr_sage_relation_f32', N.ptr(indptr), N.ptr(indices), N.ptr(edge_w) if edge_w is not None else None, nnz,
            N.ptr(h_src), N.ptr(h_dst), row_begin, row_end, d_neigh, d_self, N.ptr(w_self_t), N.ptr(w_neigh_t), d_out,
-           reducer, int(l2norm), accumulate, float(z_scale), int(flags), N.ptr(out), N.ptr(ws), ws.numel(), N.stream())
+           reducer, int(l2norm), accumulate, float(z_scale), int(flags), N.ptr(packed) if packed is not None else None,
+           N.ptr(out), N.ptr(ws), ws.numel(), N.stream())
     return out
+
+
+def sage_pack_weights(w_self_t: torch.Tensor, w_neigh_t: torch.Tensor, flags: int = 0) -> Optional[torch.Tensor]:
+    """The two projection matrices in the form the fused ConvLayer kernel reads (``gr_sage_pack_weights``); ``None`` when
+    the dimensions take the generic kernel. Pack once per weight update and pass as ``sage_relation(..., packed=)``."""
+    d_self, d_out = w_self_t.shape
+    d_neigh = w_neigh_t.shape[0]
+    nb = N.load().gr_sage_packed_weights_bytes(d_neigh, d_self, d_out)
+    if nb == 0:
+        return None
+    packed = N.workspace(nb, w_self_t.device)
+    N.call('gr_sage_pack_weights', N.ptr(w_self_t), N.ptr(w_neigh_t), d_neigh, d_self, d_out, int(flags), N.ptr(packed),
+           N.stream())
+    return packed
 
 
 def gather_reduce(indptr, indices, edge_w, h_src, reducer: int, row_begin: int = 0, row_end: Optional[int] = None,

@@ -76,11 +76,18 @@ size_t gr_sage_relation_workspace_bytes(int64_t nnz, int32_t d_neigh);
  * weight scaling; GR_SAGE_FLAG_TF32_EPILOGUE selects the tf32 hi/lo split on m16n8k8 instead. Both are fp32-accurate
  * (3 products). Per call: the library keeps no mutable global state (re-entrant, one stream per caller thread). */
 enum { GR_SAGE_FLAG_TF32_EPILOGUE = 1 };
+/* The fused kernel reads the two weight matrices pre-split and pre-packed in MMA fragment order. gr_sage_pack_weights
+ * writes that form once per weight update (gr_sage_packed_weights_bytes(...) bytes, 256-byte aligned; 0 = these
+ * dimensions take the generic kernel, nothing to pack) for the same `flags` the relation calls will use; pass it as
+ * packed_or_null. With NULL every gr_sage_relation_f32 call packs into its workspace (two extra tiny launches). */
+size_t gr_sage_packed_weights_bytes(int32_t d_neigh, int32_t d_self, int32_t d_out);
+int gr_sage_pack_weights(const float* w_self_t, const float* w_neigh_t, int32_t d_neigh, int32_t d_self, int32_t d_out,
+                         int32_t flags, void* packed, gr_stream_t stream);
 int gr_sage_relation_f32(const int32_t* indptr, const int32_t* indices, const float* edge_w_or_null, int64_t nnz,
                          const float* h_src, const float* h_dst, int64_t row_begin, int64_t row_end,
                          int32_t d_neigh, int32_t d_self, const float* w_self_t, const float* w_neigh_t,
                          int32_t d_out, int reducer, int l2norm, int accumulate, float z_scale, int32_t flags,
-                         float* out, void* ws, size_t ws_bytes, gr_stream_t stream);
+                         const void* packed_or_null, float* out, void* ws, size_t ws_bytes, gr_stream_t stream);
 
 /* The gather-reduce alone (no projection): agg[v - row_begin... indexed by v] = reduce of neighbour rows. Used to
  * report aggregation bandwidth in isolation and by tests; same kernels as above without the epilogue. */

@@ -72,7 +72,7 @@ def _cpu_kernels(grb):
         return torch.relu(y) if relu else y
 
     def sage_relation(indptr, indices, edge_w, h_src, h_dst, w_self_t, w_neigh_t, out, reducer, l2norm, accumulate=0,
-                      z_scale=1.0, row_begin=0, row_end=None):
+                      z_scale=1.0, row_begin=0, row_end=None, flags=0, packed=None):
         n = indptr.shape[0] - 1
         row_end = n if row_end is None else row_end
         deg = (indptr[1:] - indptr[:-1]).long()
@@ -98,6 +98,7 @@ def _cpu_kernels(grb):
         return out
 
     ops.csr_build, ops.linear, ops.sage_relation = csr_build, linear, sage_relation
+    ops.sage_pack_weights = lambda *a, **k: None
 
 
 def _worker_sharded(rank, world, port, ret):
