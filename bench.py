@@ -56,7 +56,7 @@ def dram_traffic(config, stage):
     with open(p) as f:
         t = json.load(f)
     e = t.get(config, {}).get(stage)
-    return None if e is None else e.get('dram_bytes')
+    return None if e is None or e.get('partial') else e.get('dram_bytes')
 
 
 def peaks():

@@ -32,9 +32,24 @@ def main():
     ap.add_argument('config')
     ap.add_argument('--steps', type=int, default=1, help='bench steps covered by the capture')
     ap.add_argument('--note', default='')
+    ap.add_argument('--scale', type=float, default=1.0, help='capture covers 1/scale of a step (e.g. one of two identical layers)')
+    ap.add_argument('--partial', action='store_true', help='capture misses launches of the step: bench.py then reports null')
     ap.add_argument('--out', default=os.path.join(ROOT, 'profiles', 'traffic.json'))
     a = ap.parse_args()
     rows = list(csv.reader(open(a.csv)))
+    rows = rows[next(i for i, r in enumerate(rows) if 'Kernel Name' in r):]
+    if 'Metric Name' in rows[0]:        # long format (`ncu --metrics ... --csv`): one row per (launch, metric) -> wide
+        c = {h: i for i, h in enumerate(rows[0])}
+        names, wide, unit = [], {}, {}
+        for r in rows[1:]:
+            if len(r) < len(rows[0]):
+                continue
+            if r[c['Metric Name']] not in names:
+                names.append(r[c['Metric Name']])
+            unit[r[c['Metric Name']]] = r[c['Metric Unit']]
+            wide.setdefault(r[c['ID']], {'Kernel Name': r[c['Kernel Name']]})[r[c['Metric Name']]] = r[c['Metric Value']]
+        rows = [['Kernel Name'] + names, [''] + [unit[n] for n in names]] + \
+               [[w['Kernel Name']] + [w.get(n, '0') for n in names] for w in wide.values()]
     hdr = rows[0]
     col = {h: i for i, h in enumerate(hdr)}
     need = ['Kernel Name', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum']
@@ -68,9 +83,11 @@ def main():
         k['ms'] += val(r, 'gpu__time_duration.sum')
     for e in out.values():
         for k in ('dram_bytes', 'kernel_ms'):
-            e[k] /= a.steps
+            e[k] = e[k] / a.steps * a.scale
         e['launches'] //= a.steps
         e['source'] = os.path.basename(a.csv)
+        e['scaled_by'] = a.scale
+        e['partial'] = bool(a.partial)
         e['note'] = a.note or 'ncu --set full --clock-control none, per step; durations are serialised cold-cache replays'
     table = json.load(open(a.out)) if os.path.exists(a.out) else {}
     table[a.config] = out
