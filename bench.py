@@ -382,6 +382,7 @@ def main():
     ap.add_argument('--parts-items', type=int, default=1, choices=[1, 2])
     ap.add_argument('--shortlist', type=int, default=32)
     ap.add_argument('--no-k-band', action='store_true')
+    ap.add_argument('--no-item-order', action='store_true', help='sweep the items in id order (A/B of RecsConfig.item_order)')
     ap.add_argument('--item-shards', type=int, default=None, help='N>1 scoring layout: N = item-range shards + owner-side top-k merge; 1 = user-range shards, replicated item table; default: shard the longer side')
     ap.add_argument('--neg-k', type=int, default=2500, help='c4: negatives per positive edge (reference default 2500)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -452,7 +453,7 @@ def main():
     resident = {'graph_csr_bytes': int(graph_bytes), 'feature_bytes': int(sum(v.numel() * 4 for v in feats_dev.values())),
                 'allocated_after_ingest_bytes': int(torch.cuda.memory_allocated() - mem0)}
     cfg = grb.RecsConfig(elem=args.elem, parts=args.parts, parts_users=args.parts_users, parts_items=args.parts_items,
-                         shortlist=args.shortlist, k_band=not args.no_k_band)
+                         shortlist=args.shortlist, k_band=not args.no_k_band, item_order=not args.no_item_order)
     uid_all = np.arange(n_users)
     layouts = ['single'] if world == 1 else (['user_shards', 'item_shards'] if args.item_shards == 1 else ['item_shards', 'user_shards'])
     if args.one_layout:

@@ -47,8 +47,11 @@ SIGNATURES = {
     'gr_score_prep': (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     'gr_score_splits': (C.c_int, [_i64, _i64]),
     'gr_score_topk_workspace_bytes': (_sz, [_i64, _i64, _i32]),
-    'gr_score_topk_tc': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp,
-                                   _i32, _vp, _vp, _vp, _sz, _vp]),
+    'gr_score_topk_tc': (C.c_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp,
+                                   _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'gr_score_item_order_workspace_bytes': (_sz, [_i64]),
+    'gr_score_item_order': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'gr_permute_rows': (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     'gr_score_band': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp]),
     'gr_rescore_topk_f32': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _f32, _vp,
                                       _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),

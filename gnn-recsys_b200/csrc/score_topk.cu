@@ -69,22 +69,20 @@ __device__ __forceinline__ uint32_t select32(const uint32_t* v, int i) { return 
 // Shortlists live in shared memory ROW-major: row t of the CTA owns ls / li [t * lst .. t * lst + S), lst = S | 1 (odd
 // pitch: conflict-free both for a thread walking its own row and for a warp reading one row with one entry per lane).
 //
-// bought_test: is `gid` one of row t's already-bought items? s_nb[t] caches the smallest bought id >= the last id looked
-// up, so the common case is one compare (ids arrive in ascending order).
-__device__ __noinline__ bool bought_test(int gid, int t, int* __restrict__ s_nb, long long b0, long long b1,
+// bought_test: is `gid` one of this row's already-bought items (bought_ids[b0, b1), ascending)? `sig` is a 64-bit
+// membership signature of the row's list built once per sweep (bit hash(id) set for every bought id): a clear bit
+// answers "no" without touching memory, whatever order the ids arrive in (the item sweep may be permuted, see
+// item_perm); only a set bit pays for the binary search.
+__device__ __forceinline__ uint32_t bought_hash(int gid) { return ((uint32_t)gid * 0x9E3779B1u) >> 26; }
+__device__ __noinline__ bool bought_test(int gid, uint64_t sig, long long b0, long long b1,
                                          const int* __restrict__ bought_ids) {
-  if (gid < s_nb[t]) return false;
+  if (((sig >> bought_hash(gid)) & 1ull) == 0) return false;
   long long lo = b0, hi = b1;  // first bought id >= gid
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
-    if (bought_ids[mid] < gid) lo = mid + 1; else hi = mid;
+    if (__ldg(bought_ids + mid) < gid) lo = mid + 1; else hi = mid;
   }
-  const bool is_bought = lo < b1 && bought_ids[lo] == gid;
-  long long nxt = lo;
-  if (is_bought)  // skip duplicates of the same id (multi-edges)
-    while (nxt < b1 && bought_ids[nxt] == gid) ++nxt;
-  s_nb[t] = nxt < b1 ? bought_ids[nxt] : 0x7fffffff;
-  return is_bought;
+  return lo < b1 && __ldg(bought_ids + lo) == gid;
 }
 
 // Warp-cooperative sorted insert of candidate (s, gid) into ONE row's shortlist (rl / ri, scores descending): lane j
@@ -136,13 +134,13 @@ __device__ __noinline__ float4 coop_insert4(float4 s4, int4 g4, int4 r4, float* 
   return make_float4(nt[0], nt[1], nt[2], nt[3]);
 }
 
-// Shared-memory plan: [A: UT x PA x KB sub-tiles][B ring: `ring` slots][shortlists][next-bought][barriers]
+// Shared-memory plan: [A: UT x PA x KB sub-tiles][B ring: `ring` slots][shortlists][barriers]
 constexpr int MAX_RING = 8;
 template <int KB, int PA, bool PAIR = false>
 struct Cfg {
   static constexpr int A_BYTES = UT * PA * KB * SUB_BYTES;
   static constexpr int SLOT_BYTES = PAIR ? SUB_BYTES / 2 : SUB_BYTES;  // a CTA of a pair holds half of every B sub-tile
-  static constexpr int TAIL_BYTES = ROWS_PER_CTA * 4 + 512;  // s_nb + barriers
+  static constexpr int TAIL_BYTES = 512;  // barriers + TMEM slot
   static int list_bytes(int S) { return (S | 1) * ROWS_PER_CTA * 8; }  // row pitch S | 1
   static int ring(int S) {
     const int r = (SMEM_LIMIT - 1024 - A_BYTES - list_bytes(S) - TAIL_BYTES) / SLOT_BYTES;
@@ -160,8 +158,8 @@ struct Cfg {
 template <int KB, int PA, int PB, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_constant__ CUtensorMap tm_items,
-                  long long n_users, long long n_items, long long item_id_base, int tiles_per_split, uint32_t idesc,
-                  const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int kk,
+                  long long n_users, long long n_items, long long item_id_base, const int* __restrict__ item_perm,
+                  int tiles_per_split, uint32_t idesc, const long long* __restrict__ bought_indptr, const int* __restrict__ bought_ids, int S, int kk,
                   const float* __restrict__ band_ptr, const int* __restrict__ user_map, int ring,
                   float* __restrict__ sl_score, int* __restrict__ sl_id, int full_pairs, int tail_c,
                   float* __restrict__ tail_score, int* __restrict__ tail_id) {
@@ -177,8 +175,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
   const int lst = S | 1;                                          // shortlist row pitch
   float* ls = reinterpret_cast<float*>(sB + ring * SLOT);  // [256][lst]
   int* li = reinterpret_cast<int*>(ls + lst * ROWS_PER_CTA);     // [256][lst]
-  int* s_nb = li + lst * ROWS_PER_CTA;                            // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_nb + ROWS_PER_CTA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(li + lst * ROWS_PER_CTA) + 7) & ~(uintptr_t)7);  // lst is odd: re-align to 8 bytes
   uint64_t* full = bars;                  // [MAX_RING]  TMA -> MMA
   uint64_t* empty = full + MAX_RING;      // [MAX_RING]  MMA -> TMA
   uint64_t* a_full = empty + MAX_RING;    // [1]
@@ -323,17 +321,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
       const long long brow = user_map != nullptr ? (long long)user_map[row] : row;
       b0 = bought_indptr[brow]; b1 = bought_indptr[brow + 1];
     }
-    {
-      long long lo = b0, hi = b1;  // first bought id >= first item id of this CTA's range
-      const long long first_id = item_id_base + (long long)tile0 * TILE_N;
-      while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if ((long long)bought_ids[mid] < first_id) lo = mid + 1; else hi = mid;
-      }
-      s_nb[t] = lo < b1 ? bought_ids[lo] : 0x7fffffff;
-    }
+    uint64_t sig = 0;  // membership signature of this row's bought list (see bought_test)
+    for (long long p = b0; p < b1; ++p) sig |= 1ull << bought_hash(__ldg(bought_ids + p));
     float tau = live ? -INFINITY : INFINITY;
-    const int id_end = (int)(item_id_base + n_items);
+    const int n_pos = (int)n_items;  // sweep positions [0, n_items): position p is item item_perm[p] (p itself without a permutation)
     __syncwarp();
     for (int j = 0; j < n_tiles; ++j) {
       const int slot = j & 1;
@@ -368,12 +359,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
           // call site per column: it runs cold, so its cost is instruction-cache lines, not instructions). The whole
           // warp enters: every lane pops its own next candidate (bought test included), then the pending candidates
           // are inserted one row at a time by all 32 lanes together.
-          const int id0 = (int)(item_id_base + (long long)(tile0 + j) * TILE_N) + c * 32;
+          const int pos0 = (tile0 + j) * TILE_N + c * 32;
           uint32_t cand = 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (__uint_as_float(v[c * 32 + i]) > tau) cand |= 1u << i;
-          if (partial) cand &= (id_end - id0 >= 32) ? 0xffffffffu : (id_end > id0 ? (1u << (id_end - id0)) - 1u : 0u);
+          if (partial) cand &= (n_pos - pos0 >= 32) ? 0xffffffffu : (n_pos > pos0 ? (1u << (n_pos - pos0)) - 1u : 0u);
           for (;;) {
             float s = 0.f;
             int gid = -1;
@@ -381,7 +372,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_con
               const int i = __ffs(cand) - 1;
               cand &= cand - 1;
               const float sv = __uint_as_float(select32(v + c * 32, i));
-              if (sv > tau && !bought_test(id0 + i, t, s_nb, b0, b1, bought_ids)) { s = sv; gid = id0 + i; break; }
+              if (sv > tau) {
+                const int g = (int)item_id_base + (item_perm != nullptr ? __ldg(item_perm + pos0 + i) : pos0 + i);
+                if (!bought_test(g, sig, b0, b1, bought_ids)) { s = sv; gid = g; break; }
+              }
             }
             uint32_t pend = __ballot_sync(0xffffffffu, gid >= 0);
             if (pend == 0) break;
@@ -452,6 +446,7 @@ __global__ void fill_empty_shortlist_kernel(float* sl_score, int* sl_id, long lo
 struct ScoreArgs {
   CUtensorMap mu, mi, mi_half;  // mi_half: 64-row boxes, the half sub-tile a CTA of a pair loads
   long long n_users, n_items, item_id_base;
+  const int* perm;          // sweep position -> item index (nullptr: identity)
   int splits, tiles_per_split;
   uint32_t ab_format;
   const long long* bptr;
@@ -511,12 +506,12 @@ int launch_score(const ScoreArgs& a, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (a.tail_c > 1) cfg.gridDim = dim3(2u * (unsigned)(a.full_pairs + (gx / 2 - a.full_pairs) * a.tail_c), 1u);
-    GR_CUDA(cudaLaunchKernelEx(&cfg, kern, a.mu, a.mi_half, a.n_users, a.n_items, a.item_id_base, a.tiles_per_split,
-                               idesc, a.bptr, a.bids, a.S, a.k, a.band, a.user_map, ring, a.sl_score, a.sl_id,
+    GR_CUDA(cudaLaunchKernelEx(&cfg, kern, a.mu, a.mi_half, a.n_users, a.n_items, a.item_id_base, a.perm,
+                               a.tiles_per_split, idesc, a.bptr, a.bids, a.S, a.k, a.band, a.user_map, ring, a.sl_score, a.sl_id,
                                a.full_pairs, a.tail_c, a.tail_score, a.tail_id));
   } else {
     kern<<<dim3(gx, (unsigned)a.splits), NUM_THREADS, smem, st>>>(a.mu, a.mi, a.n_users, a.n_items, a.item_id_base,
-                                                                  a.tiles_per_split, idesc, a.bptr, a.bids, a.S, a.k,
+                                                                  a.perm, a.tiles_per_split, idesc, a.bptr, a.bids, a.S, a.k,
                                                                   a.band, a.user_map, ring, a.sl_score, a.sl_id, 0, 1,
                                                                   nullptr, nullptr);
   }
@@ -560,8 +555,9 @@ extern "C" size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items
 }
 
 extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const uint16_t* items_q, int64_t n_items,
-                                int64_t item_id_base, int32_t d_pad, int32_t parts_users, int32_t parts_items,
-                                int32_t elem_type, const int64_t* bought_indptr_or_null,
+                                int64_t item_id_base, const int32_t* item_perm_or_null, int32_t d_pad,
+                                int32_t parts_users, int32_t parts_items, int32_t elem_type,
+                                const int64_t* bought_indptr_or_null,
                                 const int32_t* bought_ids_or_null, int32_t shortlist, int32_t k,
                                 const float* band_or_null, const int32_t* user_map_or_null, int32_t flags,
                                 float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes, gr_stream_t stream) {
@@ -598,7 +594,7 @@ extern "C" int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const 
   if (rc != GR_OK) return rc;
   rc = make_map(&a.mi_half, items_q, n_items, d_pad * parts_items, elem_type, TILE_N / 2);
   if (rc != GR_OK) return rc;
-  a.n_users = n_users; a.n_items = n_items; a.item_id_base = item_id_base;
+  a.n_users = n_users; a.n_items = n_items; a.item_id_base = item_id_base; a.perm = item_perm_or_null;
   a.splits = choose_splits(n_users, n_items);
   const int tiles = (int)((n_items + TILE_N - 1) / TILE_N);
   a.tiles_per_split = (tiles + a.splits - 1) / a.splits;

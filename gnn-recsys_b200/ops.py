@@ -130,19 +130,41 @@ def score_prep(x: torch.Tensor, center: Optional[torch.Tensor], d_pad: int, part
 
 def score_topk_tc(users_q, items_q, item_id_base: int, d_pad: int, parts_users: int, parts_items: int, elem_type: int,
                   bought_indptr, bought_ids, shortlist: int, k: Optional[int] = None, band: Optional[torch.Tensor] = None,
-                  user_map: Optional[torch.Tensor] = None, flags: int = 0):
+                  user_map: Optional[torch.Tensor] = None, flags: int = 0, item_perm: Optional[torch.Tensor] = None):
+    """``item_perm`` (int32 [n_items]): row p of ``items_q`` is item ``item_perm[p]`` (see ``score_item_order``)."""
     n_users, n_items = users_q.shape[0], items_q.shape[0]
+    assert item_perm is None or (item_perm.dtype == torch.int32 and item_perm.numel() == n_items)
     dev = users_q.device
     sl_score = torch.empty((n_users, shortlist), dtype=torch.float32, device=dev)
     sl_id = torch.empty((n_users, shortlist), dtype=torch.int32, device=dev)
     lib = N.load()
     ws = _ws(lib.gr_score_topk_workspace_bytes(n_users, n_items, shortlist), dev, 'score')
-    N.call('gr_score_topk_tc', N.ptr(users_q), n_users, N.ptr(items_q), n_items, item_id_base, d_pad, parts_users,
-           parts_items, elem_type, N.ptr(bought_indptr) if bought_indptr is not None else None,
+    N.call('gr_score_topk_tc', N.ptr(users_q), n_users, N.ptr(items_q), n_items, item_id_base,
+           N.ptr(item_perm) if item_perm is not None else None, d_pad, parts_users, parts_items, elem_type, N.ptr(bought_indptr) if bought_indptr is not None else None,
            N.ptr(bought_ids) if bought_ids is not None else None, shortlist, shortlist if k is None else k,
            N.ptr(band) if band is not None else None, N.ptr(user_map) if user_map is not None else None, flags,
            N.ptr(sl_score), N.ptr(sl_id), N.ptr(ws), ws.numel(), N.stream())
     return sl_score, sl_id
+
+
+def score_item_order(h_item: torch.Tensor, direction: torch.Tensor) -> torch.Tensor:
+    """int32 [n_items]: item indices in descending order of cos(h_item[i], direction) -- the sweep order that lets the
+    shortlist thresholds of ``score_topk_tc`` settle after the first tiles (csrc/item_order.cu)."""
+    n, d = h_item.shape
+    assert h_item.dtype == torch.float32 and h_item.is_contiguous() and direction.numel() == d
+    perm = torch.empty(n, dtype=torch.int32, device=h_item.device)
+    lib = N.load()
+    ws = _ws(lib.gr_score_item_order_workspace_bytes(n), h_item.device, 'order')
+    N.call('gr_score_item_order', N.ptr(h_item), n, d, N.ptr(direction), N.ptr(perm), N.ptr(ws), ws.numel(), N.stream())
+    return perm
+
+
+def permute_rows(x: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """``out[p] = x[perm[p]]`` for a 2-D contiguous tensor whose rows are a multiple of 16 bytes."""
+    assert x.dim() == 2 and x.is_contiguous() and perm.dtype == torch.int32 and perm.numel() == x.shape[0]
+    out = torch.empty_like(x)
+    N.call('gr_permute_rows', N.ptr(x), x.shape[0], x.shape[1] * x.element_size(), N.ptr(perm), N.ptr(out), N.stream())
+    return out
 
 
 def score_band(item_stats, user_stats, elem_type: int, parts_users: int, parts_items: int, acc_err: float) -> torch.Tensor:

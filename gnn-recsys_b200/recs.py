@@ -47,6 +47,10 @@ class RecsConfig:
     small_work: int = 1 << 31     # scheme directly with its 16-entry shortlist: a sweep that short is all shortlist
     #                               warm-up, and the single product's proof would only add a second pass (and a host
     #                               read) to a launch-bound step (c1: 10k x 5k)
+    item_order: bool = True       # sweep the items in descending order of their cosine to the mean user row (thresholds
+    #                               settle after the first tiles instead of climbing through the whole sweep; same result)
+    order_min_items: int = 16384  # ... for tables at least this long and calls of at least order_min_work scores
+    order_min_work: int = 1 << 31
     parts: Optional[int] = None   # shorthand: parts=1 -> (1, 1), parts=2 -> (2, 2) and no second pass
 
     def __post_init__(self):
@@ -193,19 +197,23 @@ class ScoringTable:
         return self._ops[key]
 
 
-def _tc_pass(h_user, table: ScoringTable, k: int, bptr, bids, scheme, cfg: RecsConfig, user_map=None, mark=None):
+def _tc_pass(h_user, table: ScoringTable, k: int, bptr, bids, scheme, cfg: RecsConfig, user_map=None, mark=None,
+             order=None):
     """One tensor-core pass: prep(users) -> GEMM + shortlist -> exact re-score + proof.
-    Returns ``(ids, scores, overflow list, n_overflow)``; overflow entries are ``user_map`` values when given."""
+    Returns ``(ids, scores, overflow list, n_overflow)``; overflow entries are ``user_map`` values when given.
+    ``order``: item sweep order (``ops.score_item_order``) or None for item-id order."""
     elem, pu, pi, shortlist = scheme
     et = elem_type_of(elem)
     shortlist = max(shortlist, k)
     items_q, item_stats = table.operands(elem, pi)
+    if order is not None:
+        items_q = ops.permute_rows(items_q, order)
     users_q, user_stats = ops.score_prep(h_user, None, table.d_pad, pu, et, cfg.k_band)
     band = ops.score_band(item_stats, user_stats, et, pu, pi, cfg.acc_err) if cfg.k_band else None
     if mark:
         mark('score_begin')
     sl_score, sl_id = ops.score_topk_tc(users_q, items_q, table.item_id_base, table.d_pad, pu, pi, et, bptr, bids,
-                                        shortlist, k, band, user_map, cfg.flags)
+                                        shortlist, k, band, user_map, cfg.flags, item_perm=order)
     if mark:
         mark('score_end')
     return ops.rescore_topk(h_user, table.h_item, table.item_id_base, table.center, sl_score, sl_id, item_stats, et, pu,
@@ -239,7 +247,11 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
     first, second = (cfg.elem, cfg.parts_users, cfg.parts_items, cfg.shortlist), cfg.second
     if second is not None and cfg.products < 3 and table.n_items < cfg.small_items and n * table.n_items < cfg.small_work:
         first, second = second, None   # short sweep: the fp32-grade scheme directly (see RecsConfig.small_items)
-    ids, scores, overflow, n_overflow = _tc_pass(h_user, table, k, bptr, bids, first, cfg, mark=mark)
+    order = None
+    if cfg.item_order and table.n_items >= cfg.order_min_items and n * table.n_items >= cfg.order_min_work:
+        # sweep order of this call: items by descending cosine to the mean normalised user row (shared by both passes)
+        order = ops.score_item_order(table.h_item, ops.colmean_normalized(h_user))
+    ids, scores, overflow, n_overflow = _tc_pass(h_user, table, k, bptr, bids, first, cfg, mark=mark, order=order)
     mark('rescore_end')
     n1 = n2 = 0
     if second is None:
@@ -255,8 +267,10 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
         if n1 > 0:
             # pass 2: the users pass 1 could not prove, compacted, through the more accurate scheme
             rows = overflow[:n1].sort().values  # ascending: deterministic whatever order the proof kernel appended in
+            # (the sweep order pays for one permutation lookup per candidate: only worth it on a long pass)
             ids2, scores2, overflow, n_overflow = _tc_pass(h_user[rows.long()], table, k, bptr, bids, second, cfg,
-                                                           user_map=rows)
+                                                           user_map=rows,
+                                                           order=order if n1 * table.n_items >= cfg.order_min_work else None)
             ids[rows.long()] = ids2
             scores[rows.long()] = scores2
             # exact fp32 pass for whoever is left (device-side list and count)

@@ -121,6 +121,10 @@ int gr_edge_cosine_f32(const int32_t* u, const int32_t* v, int64_t n_edges, cons
  *           (band: device float, NULL = +inf = plain S-th-best rule). user_map (optional int32[n_users]): row u's
  *           bought list is that of user user_map[u] (second pass over a compacted user subset). Output: per user `shortlist` approximate
  *           (centred) scores, descending, and their global item ids (-1 = empty slot).
+ *           item_perm (optional int32[n_items]): row p of items_q is item item_perm[p] (+ item_id_base) -- the item
+ *           table may be swept in any order; gr_score_item_order + gr_permute_rows build the order that lets the
+ *           thresholds settle after the first tiles (descending cosine to the mean user row). The shortlist holds
+ *           real item ids either way, so stages 2 / 3 and the result do not depend on it.
  *           flags: GR_SCORE_FLAG_SINGLE_CTA = cta_group::1 kernel instead of CTA pairs (same results);
  *           GR_SCORE_FLAG_NO_TAIL_SPLIT = do not cut the user tiles of the last, partial wave into item ranges.
  *  stage 2  gr_rescore_topk_f32: exact fp32 cosine (torch formula x.y / sqrt(max(|x|^2 |y|^2, eps^2))) of the
@@ -151,10 +155,19 @@ int gr_score_prep(const float* x, int64_t n, int32_t d, const float* center_or_n
 int gr_score_splits(int64_t n_users, int64_t n_items);
 size_t gr_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int32_t shortlist);
 int gr_score_topk_tc(const uint16_t* users_q, int64_t n_users, const uint16_t* items_q, int64_t n_items,
-                     int64_t item_id_base, int32_t d_pad, int32_t parts_users, int32_t parts_items, int32_t elem_type,
-                     const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t shortlist,
+                     int64_t item_id_base, const int32_t* item_perm_or_null, int32_t d_pad, int32_t parts_users,
+                     int32_t parts_items, int32_t elem_type, const int64_t* bought_indptr_or_null, const int32_t* bought_ids_or_null, int32_t shortlist,
                      int32_t k, const float* band_or_null, const int32_t* user_map_or_null, int32_t flags,
                      float* sl_score, int32_t* sl_id, void* ws, size_t ws_bytes, gr_stream_t stream);
+/* Item sweep order of stage 1: perm[p] = index of the item swept at position p, descending cos(h_item[i], dir)
+ * (65536 equal-width buckets between the smallest and largest cosine, ascending index inside a bucket; dir = any
+ * positive multiple of the mean normalised user row, e.g. gr_colmean_normalized_f32 of the user table).
+ * gr_permute_rows: dst[p] = src[perm[p]] for rows of row_bytes (multiple of 16; not in place). */
+size_t gr_score_item_order_workspace_bytes(int64_t n_items);
+int gr_score_item_order(const float* h_item, int64_t n_items, int32_t d, const float* dir, int32_t* perm, void* ws,
+                        size_t ws_bytes, gr_stream_t stream);
+int gr_permute_rows(const void* src, int64_t n_rows, int64_t row_bytes, const int32_t* perm, void* dst,
+                    gr_stream_t stream);
 /* *band = 2 x the largest err_u of stage 2 over a user table whose gr_score_prep statistics are user_stats4 */
 int gr_score_band(const float* item_stats4, const float* user_stats4, int32_t elem_type, int32_t parts_users,
                   int32_t parts_items, float acc_err, float* band, gr_stream_t stream);

@@ -28,9 +28,27 @@ hu = torch.nn.functional.normalize(y['user'], dim=1); hi = torch.nn.functional.n
 yc = (hi - hi.mean(0)).to(torch.float16).float()
 U0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 x = hu[U0:U0 + 256].to(torch.float16).float()
-A = (x @ yc.t()).numpy()                     # [256, I] approximate scores, item-id order
+A0 = (x @ yc.t()).numpy()                    # [256, I] approximate scores, item-id order
 k = 10
-for S, band in ((32, 6.9e-4), (32, np.inf), (16, np.inf), (24, 6.9e-4)):
+# item orderings (the kernel is free to sweep the items in any order): proxy = score against the mean user direction
+proxy = (yc @ torch.nn.functional.normalize(hu.mean(0), dim=0)).numpy()
+proxy_item = (yc @ torch.nn.functional.normalize(hi.mean(0), dim=0)).numpy()      # known when the item table is built
+rank = np.argsort(-proxy, kind='stable')
+ORDERS = {'id': np.arange(I)}
+for H in (512, 4096, 16384):
+    head = np.sort(rank[:H]); rest = np.sort(rank[H:])
+    ORDERS['head%d_by_id' % H] = np.concatenate([head, rest])
+    ORDERS['head%d_sorted' % H] = np.concatenate([rank[:H], rest])
+ORDERS['full_sort'] = rank
+for NB in (256, 1024, 4096):   # counting sort into NB equal-width proxy buckets (descending), ascending id inside a bucket
+    b = np.floor((proxy.max() - proxy) / (proxy.max() - proxy.min()) * (NB - 1)).astype(np.int64)
+    ORDERS['bucket%d' % NB] = np.argsort(b, kind='stable')
+sample = (yc @ torch.nn.functional.normalize(hu[::97].mean(0), dim=0)).numpy()   # direction from 1% of the users
+ORDERS['full_sort_sampled_users'] = np.argsort(-sample, kind='stable')
+ORDERS['full_sort_item_proxy'] = np.argsort(-proxy_item, kind='stable')
+only = sys.argv[5].split(',') if len(sys.argv) > 5 else list(ORDERS)
+for oname, S, band in [(o, 32, 6.9e-4) for o in only] + [('id', 32, np.inf), ('id', 16, np.inf), ('id', 24, 6.9e-4)]:
+    A = np.ascontiguousarray(A0[:, ORDERS[oname]])
     lists = np.full((256, S), -np.inf, dtype=np.float32)
     tau = np.full(256, -np.inf, dtype=np.float32)
     inserts = np.zeros(256, dtype=np.int64)
@@ -54,6 +72,7 @@ for S, band in ((32, 6.9e-4), (32, np.inf), (16, np.inf), (24, 6.9e-4)):
                     tau[r] = max(l[S - 1], l[k - 1] - band)
                     inserts[r] += 1
     groups = (I + 31) // 32
+    print('order=%s ' % oname, end='')
     print('S=%d band=%s: inserts/row mean %.0f max %d; warp trips per warp-sweep %.0f of %d groups (%.1f per 128-item tile); '
           'lanes pending per trip: mean %.2f, P(>=2) %.2f, P(>=4) %.2f, P(>=8) %.2f'
           % (S, band, inserts.mean(), inserts.max(), trips / 8, groups, trips / 8 / (groups / 4),

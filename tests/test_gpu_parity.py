@@ -611,6 +611,69 @@ def test_tail_wave_split_gives_the_same_shortlists(grb):
     assert float((sc - ex_sc).abs().max()) < 1e-5
 
 
+ORDERED = dict(small_items=0, order_min_items=0, order_min_work=0)   # force the permuted item sweep on small tables
+
+
+def test_item_order_is_a_descending_cosine_permutation(grb):
+    """gr_score_item_order: a permutation of the item indices, cosines to the direction non-increasing up to one bucket
+    width ((max - min) / 65535), ascending index inside a bucket; gr_permute_rows == index_select."""
+    rng = np.random.default_rng(3)
+    for n, d in ((1, 128), (100, 64), (40000, 128), (3333, 96)):
+        hi = clustered_embeddings(rng, n, d, 0.3).cuda() * torch.from_numpy(rng.uniform(0.5, 2, (n, 1)).astype(np.float32)).cuda()
+        if n > 10:
+            hi[5] = 0.0        # an all-zero row: cosine 0, must not break the range
+        direction = torch.from_numpy(rng.standard_normal(d).astype(np.float32)).cuda()
+        perm = grb.ops.score_item_order(hi, direction)
+        assert perm.dtype == torch.int32 and sorted(perm.tolist()) == list(range(n))
+        cos = (hi.double() @ direction.double()) / hi.double().norm(dim=1).clamp_min(1e-12)
+        c = cos[perm.long()]
+        width = float(cos.max() - cos.min()) / 65535
+        assert bool((c[1:] <= c[:-1] + width * 1.01 + 1e-4).all())   # fp32 dot products of the kernel vs fp64 here
+        q = torch.from_numpy(rng.integers(-2 ** 15, 2 ** 15, (n, 2 * d)).astype(np.int16)).cuda()
+        assert torch.equal(grb.ops.permute_rows(q, perm), q[perm.long()])
+    same = torch.ones(500, 128, device='cuda')           # all cosines equal: the identity order
+    assert grb.ops.score_item_order(same, torch.ones(128, device='cuda')).tolist() == list(range(500))
+
+
+@pytest.mark.parametrize('cfg', [dict(ORDERED), dict(ORDERED, single_cta=True), dict(ORDERED, shortlist=12),
+                                 dict(ORDERED, elem='bf16', second=('bf16', 2, 2, 16)), dict(ORDERED, parts=2)],
+                         ids=['pair', 'single_cta', 'S12', 'bf16', 'three-product'])
+@pytest.mark.parametrize('shape', [(1000, 20000), (45000, 20000), (257, 129), (5, 40)])
+def test_recs_with_permuted_item_sweep(grb, shape, cfg):
+    """The item table swept in descending-cosine order (RecsConfig.item_order): identical recommendations, bought
+    lists honoured although the ids no longer arrive in ascending order (tail-wave split included: 45 000 users)."""
+    _recs_large(grb, shape, grb.RecsConfig(**cfg))
+
+
+def test_permuted_sweep_inserts_less_and_returns_the_same_shortlist_heads(grb):
+    """Kernel-level: same users / items, identity vs permuted sweep -> the first k shortlist entries (score, id) are
+    identical; users with LONG bought lists (300 ids, among them their best items) stay filtered."""
+    rng = np.random.default_rng(8)
+    n_u, n_i, d, k = 3000, 30000, 128, 10
+    hu, hi = clustered_embeddings(rng, n_u, d, 0.2).cuda(), clustered_embeddings(rng, n_i, d, 0.2).cuda()
+    c = grb.RecsConfig(small_items=0)
+    table = grb.ScoringTable(hi, c)
+    best = (torch.nn.functional.normalize(hu, dim=1) @ torch.nn.functional.normalize(hi, dim=1).t()).topk(40, dim=1).indices.cpu().numpy()
+    bu, bi = [], []
+    for u in range(n_u):
+        ids = np.unique(np.concatenate([best[u, :20], rng.integers(0, n_i, 300 if u % 7 == 0 else 3)]))
+        bu.append(np.full(ids.size, u)); bi.append(ids)
+    bought = grb.BoughtCSR.from_edges(np.concatenate(bu), np.concatenate(bi), n_u)
+    bptr, bids = bought.on(hu.device)
+    uq, ust = grb.ops.score_prep(hu, None, 128, 1, c.elem_type, True)
+    perm = grb.ops.score_item_order(hi, grb.ops.colmean_normalized(hu))
+    a_s, a_i = grb.ops.score_topk_tc(uq, table.items_q, 0, 128, 1, 1, c.elem_type, bptr, bids, 32, 10, None)
+    b_s, b_i = grb.ops.score_topk_tc(uq, grb.ops.permute_rows(table.items_q, perm), 0, 128, 1, 1, c.elem_type, bptr, bids,
+                                     32, 10, None, item_perm=perm)
+    assert torch.equal(a_s, b_s)                       # plain S-th-best rule: the 32 best scores do not depend on the order
+    assert torch.equal(a_i.sort(dim=1).values[a_s.diff(dim=1).ne(0).all(1)], b_i.sort(dim=1).values[a_s.diff(dim=1).ne(0).all(1)])
+    for r in range(0, n_u, 97):
+        assert not set(b_i[r].tolist()) & set(bought[r])
+    ids, sc = grb.recommend_topk(hu, grb.ScoringTable(hi, grb.RecsConfig(**ORDERED)), k, bought)
+    ex_ids, ex_sc = grb.recommend_topk(hu, grb.ScoringTable(hi, grb.RecsConfig(exact_only=True)), k, bought)
+    assert float((sc - ex_sc).abs().max()) < 1e-5
+
+
 def _recs_large(grb, shape, cfg, tables=None):
     n_u, n_i = shape
     rng = np.random.default_rng(n_u)

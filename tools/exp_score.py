@@ -45,7 +45,7 @@ for kw in SCHEMES:
         mark('t1')
     torch.cuda.synchronize()
     ms = ev['score_begin'].elapsed_time(ev['score_end'])
-    r = dict(cfg=kw, kernel_ms=round(ms, 3), total_ms=round(ev['t0'].elapsed_time(ev['t1']), 3),
+    r = dict(cfg=kw, kernel_ms=round(ms, 3), prep_ms=round(ev['t0'].elapsed_time(ev['score_begin']), 3), total_ms=round(ev['t0'].elapsed_time(ev['t1']), 3),
              rescore_ms=round(ev['score_end'].elapsed_time(ev['rescore_end']), 3),
              second_ms=round(ev['rescore_end'].elapsed_time(ev['fallback_end']), 3), overflow=n_over,
              useful_tflops=round(flops / ms / 1e9, 1), executed_tflops=round(flops * cfg.products / ms / 1e9, 1))
