@@ -22,7 +22,7 @@ STAGES = [  # first match wins
                   r'pack_weights|weight_scale_kernel|linear_tc5_kernel|split_rows_f16_kernel|split_weights_f16_kernel|linear_tc_kernel'),
     ('embed_in', r'linear_small'),
     ('rescore', r'rescore_kernel|exact_topk_kernel|topk_merge_kernel'),
-    ('prep', r'score_prep_kernel|colmean|score_band_kernel'),
+    ('prep', r'score_prep_kernel|colmean|score_band_kernel|order_\w+_kernel|permute_rows_kernel|radix_\w+_kernel|scan_kernel|csr_finish_kernel'),
 ]
 
 
