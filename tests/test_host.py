@@ -365,3 +365,47 @@ def test_device_block_builder_host_logic_with_oracle_kernels(monkeypatch):
         for c in g.canonical_etypes:
             assert x.rels[c].indices.tolist() == y.rels[c].indices.tolist()
             assert torch.equal(x.rels[c].weight, y.rels[c].weight)
+
+
+def test_bench_tensor_peak_follows_the_measured_clock():
+    """bench.py reports the scoring kernel against the cuBLAS figure of the clock regime the run was in: burst when the
+    median SM clock under load is nearer the maximum than the clock the sustained figure was measured at."""
+    import bench
+    pk = dict(hbm=6552.0, tc_burst=1661.5, tc=1389.2, source='measured', sustained_mhz=1350.0, max_mhz=1965.0)
+    assert bench.tensor_peak(pk, {'sm_mhz': 1875.0, 'sm_max_mhz': 1965.0})[0] == 1661.5
+    peak, label = bench.tensor_peak(pk, {'sm_mhz': 1530.0, 'sm_max_mhz': 1965.0})
+    assert peak == 1389.2 and 'sustained' in label
+    assert bench.tensor_peak(pk, None)[0] == 1389.2                       # no clock samples: the conservative figure
+    fb = dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, source='fallback', sustained_mhz=None, max_mhz=None)
+    assert bench.tensor_peak(fb, {'sm_mhz': 1900.0, 'sm_max_mhz': 1965.0})[0] == 1590.0
+    assert bench.tensor_peak(fb, {'sm_mhz': 1300.0, 'sm_max_mhz': 1965.0})[0] == 1400.0
+
+
+def test_ncu_traffic_tool_reads_wide_and_long_csv(tmp_path):
+    """tools/ncu_traffic.py: per-stage DRAM bytes from an `ncu --page raw --csv` (wide) or `ncu --metrics ... --csv`
+    (long) capture; a partial capture makes bench.dram_traffic() return None instead of an undercount."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    wide = tmp_path / 'wide.csv'
+    wide.write_text('"ID","Kernel Name","dram__bytes_read.sum","dram__bytes_write.sum","gpu__time_duration.sum"\n'
+                    '"","","byte","byte","ns"\n'
+                    '"0","void <unnamed>::sage_fused_kernel<1, 1, 4, 2, 0, 1>(int)","1000","500","2000000"\n'
+                    '"1","void <unnamed>::score_topk_kernel<2, 1, 1, 1>(int)","300","100","30000000"\n'
+                    '"2","<unnamed>::order_cosine_kernel(int)","40","2","1000"\n')
+    long_ = tmp_path / 'long.csv'
+    rows = ['"ID","Kernel Name","Metric Name","Metric Unit","Metric Value"']
+    for i, (name, rd, wr, ns) in enumerate([('void <unnamed>::long_partial_kernel<1, 0>(int)', 7000, 10, 4000000),
+                                            ('<unnamed>::rescore_kernel(int)', 50, 5, 2000000)]):
+        for m, u, v in (('dram__bytes_read.sum', 'byte', rd), ('dram__bytes_write.sum', 'byte', wr),
+                        ('gpu__time_duration.sum', 'ns', ns)):
+            rows.append('"%d","%s","%s","%s","%s"' % (i, name, m, u, format(v, ',')))
+    long_.write_text('==PROF== noise line\n' + '\n'.join(rows) + '\n')
+    out = tmp_path / 'traffic.json'
+    tool = os.path.join(root, 'tools', 'ncu_traffic.py')
+    subprocess.run([sys.executable, tool, str(wide), 'cA', '--out', str(out)], check=True, capture_output=True)
+    subprocess.run([sys.executable, tool, str(long_), 'cB', '--partial', '--out', str(out)], check=True, capture_output=True)
+    t = json.loads(out.read_text())
+    assert t['cA']['aggregate']['dram_bytes'] == 1500 and t['cA']['score']['dram_bytes'] == 400
+    assert t['cA']['prep']['dram_bytes'] == 42 and abs(t['cA']['score']['kernel_ms'] - 30.0) < 1e-9
+    assert t['cB']['aggregate']['dram_bytes'] == 7010 and t['cB']['rescore']['launches'] == 1
+    assert t['cB']['aggregate']['partial'] is True and t['cA']['aggregate']['partial'] is False
