@@ -248,7 +248,7 @@ def recommend_topk(h_user: torch.Tensor, table: ScoringTable, k: int, bought: Op
     if second is not None and cfg.products < 3 and table.n_items < cfg.small_items and n * table.n_items < cfg.small_work:
         first, second = second, None   # short sweep: the fp32-grade scheme directly (see RecsConfig.small_items)
     order = None
-    if cfg.item_order and table.n_items >= cfg.order_min_items and n * table.n_items >= cfg.order_min_work:
+    if cfg.item_order and n > 0 and table.n_items >= max(cfg.order_min_items, 1) and n * table.n_items >= cfg.order_min_work:
         # sweep order of this call: items by descending cosine to the mean normalised user row (shared by both passes)
         order = ops.score_item_order(table.h_item, ops.colmean_normalized(h_user))
     ids, scores, overflow, n_overflow = _tc_pass(h_user, table, k, bptr, bids, first, cfg, mark=mark, order=order)
